@@ -1,0 +1,191 @@
+/*
+ * sifnn.h -- C-ABI of libsifnn_b200.so: the SIF-NN-SR ModelB hot path as hand-written
+ * sm_100a CUDA kernels.
+ *
+ * The reference (cgranerob/Land-Surface-Temperature-Super-Resolution-...) has no FFI of
+ * its own: its hot path is a stack of PyTorch library calls.  Each entry point below
+ * names the reference call site (file:line, relative to the reference root) it
+ * replaces.  All pointers are DEVICE pointers to fp32, NCHW-contiguous data unless the
+ * parameter is documented as "host".  The caller (PyTorch) owns every buffer, including
+ * workspaces; the library never allocates or frees device memory, never synchronises the
+ * host, and launches everything on the given stream.
+ *
+ * Return value: 0 on success, otherwise a non-zero code (cudaError_t value for CUDA
+ * failures, SIFNN_EINVAL for bad arguments); sifnn_last_error() returns a thread-local
+ * message.  There is no CPU fallback.
+ */
+#ifndef SIFNN_H
+#define SIFNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sifnn_stream_t; /* cudaStream_t */
+
+#define SIFNN_EINVAL 10001
+#define SIFNN_VERSION 1
+
+int sifnn_version(void);
+const char* sifnn_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * Per-op entry points
+ * ---------------------------------------------------------------------------------- */
+
+/* nn.Conv2d(k=3, padding=1, padding_mode='replicate') forward  (model.py:135,138,507,605).
+ * in  (B,Cin,H,W); the consumer-side prologue optionally applies the previous layer's
+ * BatchNorm+ReLU on load: v = max(in*in_scale[c] + in_shift[c], 0)  (model.py:136-137);
+ * pass NULL/NULL for a plain input.   w (Cout,Cin,3,3); bias (Cout) or NULL.
+ * out (B,Cout,H,W) receives the raw (pre-BatchNorm) convolution.
+ * stats: NULL, or 2*Cout doubles that receive += (sum, sum of squares) of `out` per
+ * channel -- the BatchNorm batch statistics (model.py:136) gathered in the epilogue. */
+int sifnn_conv3x3_fwd(const float* in, const float* in_scale, const float* in_shift,
+                      const float* w, const float* bias, float* out, double* stats,
+                      int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+
+/* Data gradient of the same convolution (autograd of model.py:135; loss.backward() at
+ * train_model_B_gradFTM.py:119).  dy (B,Cout,H,W) -> dx (B,Cin,H,W), including the
+ * adjoint of the replicate padding.  accumulate != 0 adds into dx. */
+int sifnn_conv3x3_dgrad(const float* dy, const float* w, float* dx, int accumulate,
+                        int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+
+/* Weight gradient.  `in`/in_scale/in_shift as in sifnn_conv3x3_fwd.  dw (Cout,Cin,3,3)
+ * is overwritten; dbias (Cout) or NULL.  workspace: sifnn_conv3x3_wgrad_workspace()
+ * bytes of scratch (per-CTA partial sums, reduced in a fixed order -> deterministic). */
+size_t sifnn_conv3x3_wgrad_workspace(int B, int Cin, int Cout, int H, int W);
+int sifnn_conv3x3_wgrad(const float* in, const float* in_scale, const float* in_shift,
+                        const float* dy, float* dw, float* dbias, void* workspace,
+                        int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+
+/* nn.BatchNorm2d training statistics -> affine (model.py:136,139,508).
+ * stats (2*C doubles: sum, sumsq over n = B*H*W).  Writes scale = gamma*invstd,
+ * shift = beta - mean*scale, save_mean, save_invstd (each C floats) and, if
+ * running_mean != NULL, updates the running buffers with momentum 0.1 and the unbiased
+ * variance.  eps = 1e-5. */
+int sifnn_bn_train_finalize(const double* stats, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var,
+                            float* scale, float* shift, float* save_mean, float* save_invstd,
+                            int C, double n, sifnn_stream_t stream);
+
+/* nn.BatchNorm2d eval: scale/shift from the running buffers. */
+int sifnn_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
+                         const float* running_var, float* scale, float* shift, int C,
+                         sifnn_stream_t stream);
+
+/* BatchNorm+ReLU backward (autograd of model.py:136-137), two passes.
+ * reduce: sums (2*C doubles, zeroed by the caller) += (sum dy, sum dy*xhat), with
+ *         dy = dY * (raw*scale+shift > 0), xhat = (raw-mean)*invstd.
+ * apply : dx = gamma*invstd*(dy - sum_dy/n - xhat*sum_dy_xhat/n); dgamma = sum dy*xhat,
+ *         dbeta = sum dy.  dx may alias dY. */
+int sifnn_bn_relu_bwd_reduce(const float* dY, const float* raw, const float* scale, const float* shift,
+                             const float* save_mean, const float* save_invstd, double* sums,
+                             int B, int C, int HW, sifnn_stream_t stream);
+int sifnn_bn_relu_bwd_apply(const float* dY, const float* raw, const float* scale, const float* shift,
+                            const float* save_mean, const float* save_invstd, const float* gamma,
+                            const double* sums, float* dx, float* dgamma, float* dbeta,
+                            int B, int C, int HW, sifnn_stream_t stream);
+
+/* AvgPool2d(2,2) of relu(raw*scale+shift)  (model.py:504,529) and its adjoint. */
+int sifnn_act_avgpool2_fwd(const float* raw, const float* scale, const float* shift, float* out,
+                           int B, int C, int H, int W, sifnn_stream_t stream);
+int sifnn_avgpool2_bwd(const float* dout, float* din, int accumulate,
+                       int B, int C, int H, int W, sifnn_stream_t stream);
+
+/* ResidualConnection: out = x + relu(raw*scale+shift)  (model.py:311-312). */
+int sifnn_act_residual_fwd(const float* x, const float* raw, const float* scale, const float* shift,
+                           float* out, int B, int C, int HW, sifnn_stream_t stream);
+
+/* UpBlock head: out = cat([bilinear_x2(relu(low)), relu(skip)], 1), align_corners=True
+ * (model.py:207,236,247).  low (B,C1,H,W) raw + its affine; skip (B,C2,2H,2W) raw + affine. */
+int sifnn_act_upcat_fwd(const float* low, const float* low_scale, const float* low_shift,
+                        const float* skip, const float* skip_scale, const float* skip_shift,
+                        float* out, int B, int C1, int C2, int H, int W, sifnn_stream_t stream);
+/* Adjoint: dlow (B,C1,H,W) = up2^T(dout[:, :C1]); dskip (B,C2,2H,2W) = dout[:, C1:]. */
+int sifnn_upcat_bwd(const float* dout, float* dlow, float* dskip,
+                    int B, int C1, int C2, int H, int W, sifnn_stream_t stream);
+
+/* Input preparation: x[:,0] = bicubic_x4(lst) (cv2.INTER_CUBIC, utils.py:163-180),
+ * x[:,1] = ndvi  (torch.cat at train_model_B_gradFTM.py:94 / predict.py:101).
+ * lst (B,1,h,w), ndvi (B,1,4h,4w), x (B,2,4h,4w). */
+int sifnn_bicubic4_cat(const float* lst, const float* ndvi, float* x, int B, int h, int w,
+                       sifnn_stream_t stream);
+
+/* Fused loss forward + dLoss/dSR.
+ * kind 1 = SR1 (train_model_B_predef_filters.py:111-133: Huber(downscale) + Huber(Sobel4)),
+ * kind 2 = SR2 (train_model_B_gradFTM.py:99-117: Huber(downscale) + Huber(x - G_0.25(x))).
+ * sr, ndvi (B,1,H,W); lst (B,1,H/4,W/4).
+ * tab_ds : H x 3   per-axis ADJOINT weights of (blur mtf 0.1 + bicubic/4): tab_ds[r][i] is the weight of
+ *                   SR row r in low-res row r/4-1+i (reflection folded in).  Built on the host, lives on device.
+ * h12    : 12      forward taps of the same operator: D[I] = sum_t h12[t] * SR[reflect(4I-4+t)]
+ * tab_lp : H x 9   per-axis adjoint weights of the reflect-padded G_0.25 blur (SR2 only, else NULL)
+ * g9     : 9       taps of G_0.25 (SR2 only, else NULL)
+ * losses : 3 doubles, zeroed by the caller: += (ds, percep, alpha*ds+(1-alpha)*percep)
+ * dsr    : (B,1,H,W) gradient of the total loss, or NULL for loss only.
+ * Requires H == W and H % 64 == 0.  The un-normalise / re-normalise pair around the down-scaling
+ * cancels exactly (the weights sum to one), so mean/std are not parameters. */
+int sifnn_loss_fwd_bwd(int kind, const float* sr, const float* ndvi, const float* lst,
+                       const float* tab_ds, const float* h12, const float* tab_lp, const float* g9,
+                       float alpha, float gamma, double* losses, float* dsr,
+                       int B, int H, int W, sifnn_stream_t stream);
+
+/* torch.optim.Adam(lr) step (train_model_B_gradFTM.py:453,121) over one flat buffer.
+ * step_count: device int64, incremented by the kernel launch. grad_scale multiplies g first. */
+int sifnn_adam_step(float* p, const float* g, float* m, float* v, int64_t* step_count,
+                    double lr, double beta1, double beta2, double eps, float grad_scale,
+                    int64_t n, sifnn_stream_t stream);
+
+/* Measured fp32 FMA peak helper (roofline denominator for the SIMT kernels): runs a
+ * register-resident FFMA loop; writes total FLOPs issued to *flops_out (host). */
+int sifnn_fp32_peak_kernel(float* sink, int iters, double* flops_out, sifnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Whole-network entry points (ModelB_2.forward, model.py:608-645, and its autograd)
+ * ---------------------------------------------------------------------------------- */
+
+typedef struct {
+    int in_channels; /* 2 */
+    int down[4];     /* 16,32,64,128 */
+} sifnn_modelb_cfg;
+
+#define SIFNN_MODELB_NCONV 18
+#define SIFNN_MODELB_NBN 17
+
+/* Offsets (in floats) of every tensor inside the flat parameter buffer, in
+ * module.parameters() order: conv weight, then (gamma, beta) per BatchNorm layer; outlay
+ * weight, outlay bias.  w_off[18], gamma_off[17], beta_off[17]; returns total floats
+ * (282705 for the shipped configuration).  bn_off[17]: offset of each layer's channel
+ * block inside the flat running_mean / running_var buffers; *bn_total = sum of C. */
+int64_t sifnn_modelb_param_layout(const sifnn_modelb_cfg* cfg, int64_t* w_off, int64_t* gamma_off,
+                                  int64_t* beta_off, int64_t* bias_off, int64_t* bn_off, int64_t* bn_total);
+
+/* Bytes of workspace for a chunk of B patches of H x W.  train != 0 keeps everything the
+ * backward pass needs. */
+size_t sifnn_modelb_workspace_bytes(const sifnn_modelb_cfg* cfg, int B, int H, int W, int train);
+
+/* Forward.  params: flat parameter buffer; running_mean / running_var: flat BN buffers.
+ * train != 0: batch statistics, running buffers updated in place (num_batches_tracked is
+ * the caller's job).  x (B,in_channels,H,W) -> y (B,1,H,W). */
+int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* params, float* running_mean,
+                         float* running_var, const float* x, float* y, void* workspace,
+                         int B, int H, int W, int train, sifnn_stream_t stream);
+
+/* Backward of the last train-mode forward that used `workspace`.  dy (B,1,H,W);
+ * grads: flat buffer laid out like params, overwritten.
+ * phase: 0 = whole backward, 1 = decoder half only (ub3..ub1 + outlay gradients are final
+ * afterwards), 2 = encoder half (must follow phase 1).  Splitting lets the host start the
+ * all-reduce of the decoder bucket while the encoder half runs. */
+int sifnn_modelb_backward(const sifnn_modelb_cfg* cfg, const float* params, const float* x,
+                          const float* dy, float* grads, void* workspace,
+                          int B, int H, int W, int phase, sifnn_stream_t stream);
+
+/* Offset (floats) in the flat parameter buffer where the decoder bucket starts. */
+int64_t sifnn_modelb_decoder_offset(const sifnn_modelb_cfg* cfg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIFNN_H */

@@ -1,0 +1,17 @@
+"""B200-native SIF-NN-SR ModelB hot path (inference, SR1/SR2 training step, Adam, data
+parallelism).  Host side: Python/PyTorch for device memory, streams and
+``torch.distributed``; arithmetic: hand-written sm_100a CUDA in ``libsifnn_b200.so``
+behind the C-ABI of ``include/sifnn.h``.  No Triton, no multi-backend dispatch, no CPU
+fallback.
+
+The directory name is fixed by the build contract and is not a Python identifier; import
+it as ``sifnn_b200`` (see ``sifnn_b200.py`` at the repository root), or use the
+repository-root ``model.py`` for reference-compatible ``from model import ModelB_2``.
+"""
+from ._lib import SifnnError, build, load, LIB_PATH  # noqa: F401
+from .model import (ModelB_2, DoubleConvolution, UpBlock, ResidualConnection, DownBlock_pool, DownBlock,  # noqa: F401
+                    ResBridgeBlock, Serf, activation_functions, bicubic4_cat)
+from .losses import sr_losses, sr1_losses, sr2_losses, loss_fwd_bwd  # noqa: F401
+from .trainer import Trainer  # noqa: F401
+
+__version__ = "0.1.0"

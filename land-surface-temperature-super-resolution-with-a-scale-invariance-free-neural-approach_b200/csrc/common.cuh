@@ -1,0 +1,52 @@
+// Shared helpers for libsifnn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/sifnn.h"
+
+namespace sifnn {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+int num_sms();
+
+inline cudaStream_t as_stream(sifnn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float act_affine_relu(float x, float sc, float sh) { return fmaxf(fmaf(x, sc, sh), 0.0f); }
+
+}  // namespace sifnn
+
+#define SIFNN_REQUIRE(cond, ...)            \
+    do {                                    \
+        if (!(cond)) {                      \
+            sifnn::set_error(__VA_ARGS__);  \
+            return SIFNN_EINVAL;            \
+        }                                   \
+    } while (0)
+
+#define SIFNN_CUDA(expr)                                                         \
+    do {                                                                         \
+        cudaError_t e__ = (expr);                                                \
+        if (e__ != cudaSuccess) {                                                \
+            sifnn::set_error("%s failed: %s", #expr, cudaGetErrorString(e__));   \
+            return (int)e__;                                                     \
+        }                                                                        \
+    } while (0)
+
+#define SIFNN_TRY(expr)          \
+    do {                         \
+        int r__ = (expr);        \
+        if (r__ != 0) return r__; \
+    } while (0)

@@ -1,0 +1,68 @@
+// Error reporting, device queries and the fp32 peak probe.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+
+namespace sifnn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace sifnn
+
+extern "C" int sifnn_version(void) { return SIFNN_VERSION; }
+extern "C" const char* sifnn_last_error(void) { return sifnn::g_err; }
+
+namespace {
+// 8 independent FFMA chains per thread, operands in registers: measures the fp32
+// CUDA-core roof the SIMT convolutions are judged against (SURVEY section 8d asks the
+// builder to measure it; it is not in MEASURED_PEAKS.json).
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* sink, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.9999f + blockIdx.x * 1e-9f, c = 1e-4f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    const float r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456f) sink[0] = r;
+}
+}  // namespace
+
+extern "C" int sifnn_fp32_peak_kernel(float* sink, int iters, double* flops_out, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(sink && iters > 0, "fp32_peak: bad arguments");
+    const int blocks = sifnn::num_sms() * 8, threads = 256;
+    fp32_peak_kernel<<<blocks, threads, 0, sifnn::as_stream(stream)>>>(sink, iters);
+    if (flops_out) *flops_out = 2.0 * 128.0 * (double)iters * blocks * threads;
+    return sifnn::check_launch("fp32_peak_kernel");
+}

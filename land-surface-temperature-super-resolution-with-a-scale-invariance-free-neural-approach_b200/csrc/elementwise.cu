@@ -1,0 +1,437 @@
+// HBM-bound glue of the ModelB hot path: BatchNorm statistics / backward, AvgPool,
+// residual add, bilinear(align_corners) up-sample + concat and their adjoints, and the
+// bicubic x4 + concat input stage.  All kernels are streaming: coalesced (float4 where
+// alignment allows), grid-stride, grid sized as a multiple of the SM count.
+#include "common.cuh"
+
+namespace {
+
+inline int grid_for(long long work_items, int threads, int max_blocks_per_sm = 16) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = (long long)sifnn::num_sms() * max_blocks_per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm (model.py:136,139,508): finalize training statistics / eval affine
+// ------------------------------------------------------------------------------------------
+__global__ void bn_train_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float* running_mean, float* running_var,
+                                         float* scale, float* shift, float* save_mean, float* save_invstd, int C, double n) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = stats[c] / n;
+    double var = stats[C + c] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + 1e-5));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = fmaf(-(float)mean, sc, beta[c]);
+    save_mean[c] = (float)mean;
+    save_invstd[c] = invstd;
+    if (running_mean) {
+        const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+        running_mean[c] = (float)(0.9 * (double)running_mean[c] + 0.1 * mean);
+        running_var[c] = (float)(0.9 * (double)running_var[c] + 0.1 * unbiased);
+    }
+}
+
+__global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float* scale, float* shift, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float invstd = 1.0f / sqrtf(rv[c] + 1e-5f);
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = fmaf(-rm[c], sc, beta[c]);
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm + ReLU backward
+// ------------------------------------------------------------------------------------------
+// grid = (chunks, C, B); each CTA reduces a slice of one (b, c) plane.
+__global__ void __launch_bounds__(256) bn_relu_bwd_reduce_kernel(const float* __restrict__ dY, const float* __restrict__ raw,
+                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                 double* sums, int C, int HW) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
+    const size_t base = ((size_t)b * C + c) * HW;
+    const float4* g4 = reinterpret_cast<const float4*>(dY + base);
+    const float4* x4 = reinterpret_cast<const float4*>(raw + base);
+    float s1 = 0.f, s2 = 0.f;
+    const int n4 = HW >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const float4 g = __ldg(g4 + i), x = __ldg(x4 + i);
+        const float gv[4] = {g.x, g.y, g.z, g.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float d = fmaf(xv[j], sc, sh) > 0.f ? gv[j] : 0.f;
+            s1 += d;
+            s2 = fmaf(d, (xv[j] - mu) * is, s2);
+        }
+    }
+    __shared__ float r1[8], r2[8];
+    s1 = sifnn::warp_sum(s1);
+    s2 = sifnn::warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double d1 = 0.0, d2 = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { d1 += (double)r1[i]; d2 += (double)r2[i]; }
+        atomicAdd(sums + c, d1);
+        atomicAdd(sums + C + c, d2);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __restrict__ dY, const float* __restrict__ raw,
+                                                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, const double* __restrict__ sums,
+                                                                float* dx, float* dgamma, float* dbeta, int C, int HW, double inv_n) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
+    const float m1 = (float)(sums[c] * inv_n), m2 = (float)(sums[C + c] * inv_n);
+    const float gi = gamma[c] * is;
+    if (b == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        if (dbeta) dbeta[c] = (float)sums[c];
+        if (dgamma) dgamma[c] = (float)sums[C + c];
+    }
+    const size_t base = ((size_t)b * C + c) * HW;
+    const float4* g4 = reinterpret_cast<const float4*>(dY + base);
+    const float4* x4 = reinterpret_cast<const float4*>(raw + base);
+    float4* o4 = reinterpret_cast<float4*>(dx + base);
+    const int n4 = HW >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const float4 g = g4[i], x = __ldg(x4 + i);
+        const float gv[4] = {g.x, g.y, g.z, g.w}, xv[4] = {x.x, x.y, x.z, x.w};
+        float ov[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float d = fmaf(xv[j], sc, sh) > 0.f ? gv[j] : 0.f;
+            const float xh = (xv[j] - mu) * is;
+            ov[j] = gi * (d - m1 - xh * m2);
+        }
+        o4[i] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// AvgPool2d(2) of the activated tensor (model.py:504,529) and its adjoint
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) act_avgpool2_kernel(const float* __restrict__ raw, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, float* __restrict__ out,
+                                                           long long total, int C, int H, int W) {
+    const int Ho = H >> 1, Wo = W >> 1, Wo2 = Wo >> 1;  // each thread: 2 output pixels = 4 input columns
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int xo2 = (int)(idx % Wo2);
+        const int yo = (int)((idx / Wo2) % Ho);
+        const long long bc = idx / ((long long)Wo2 * Ho);
+        const int c = (int)(bc % C);
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        const float* p = raw + (size_t)bc * H * W + (size_t)(2 * yo) * W + 4 * xo2;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p + W));
+        float2 o;
+        o.x = 0.25f * (((sifnn::act_affine_relu(a.x, sc, sh) + sifnn::act_affine_relu(a.y, sc, sh)) + sifnn::act_affine_relu(b.x, sc, sh)) + sifnn::act_affine_relu(b.y, sc, sh));
+        o.y = 0.25f * (((sifnn::act_affine_relu(a.z, sc, sh) + sifnn::act_affine_relu(a.w, sc, sh)) + sifnn::act_affine_relu(b.z, sc, sh)) + sifnn::act_affine_relu(b.w, sc, sh));
+        *reinterpret_cast<float2*>(out + (size_t)bc * Ho * Wo + (size_t)yo * Wo + 2 * xo2) = o;
+    }
+}
+
+// din (B,C,H,W) (+)= 0.25 * dout (B,C,H/2,W/2) replicated 2x2
+__global__ void __launch_bounds__(256) avgpool2_bwd_kernel(const float* __restrict__ dout, float* din, long long total, int H, int W, int accumulate) {
+    const int Ho = H >> 1, Wo = W >> 1, Wo2 = Wo >> 1;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int xo2 = (int)(idx % Wo2);
+        const int yo = (int)((idx / Wo2) % Ho);
+        const long long bc = idx / ((long long)Wo2 * Ho);
+        const float2 g = __ldg(reinterpret_cast<const float2*>(dout + (size_t)bc * Ho * Wo + (size_t)yo * Wo + 2 * xo2));
+        const float gx = 0.25f * g.x, gy = 0.25f * g.y;
+        float* p = din + (size_t)bc * H * W + (size_t)(2 * yo) * W + 4 * xo2;
+        float4 a = make_float4(gx, gx, gy, gy), b = a;
+        if (accumulate) {
+            const float4 pa = *reinterpret_cast<float4*>(p), pb = *reinterpret_cast<float4*>(p + W);
+            a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+            b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+        }
+        *reinterpret_cast<float4*>(p) = a;
+        *reinterpret_cast<float4*>(p + W) = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Residual add (model.py:311-312)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) act_residual_kernel(const float* __restrict__ x, const float* __restrict__ raw,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           float* __restrict__ out, long long total4, int C, int HW4) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((idx / HW4) % C);
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x) + idx);
+        const float4 r = __ldg(reinterpret_cast<const float4*>(raw) + idx);
+        float4 o;
+        o.x = a.x + sifnn::act_affine_relu(r.x, sc, sh);
+        o.y = a.y + sifnn::act_affine_relu(r.y, sc, sh);
+        o.z = a.z + sifnn::act_affine_relu(r.z, sc, sh);
+        o.w = a.w + sifnn::act_affine_relu(r.w, sc, sh);
+        reinterpret_cast<float4*>(out)[idx] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bilinear x2 (align_corners=True) + concat (model.py:207,236,247) and adjoint
+// ------------------------------------------------------------------------------------------
+struct UpCoord { int i0, i1; float w0, w1; };
+__device__ __forceinline__ UpCoord up_coord(int dst, int n_in, float rscale) {
+    // ATen area_pixel_compute_source_index(align_corners=true): src = scale * dst, scale = (in-1)/(out-1) in fp32
+    const float s = rscale * (float)dst;
+    UpCoord u;
+    u.i0 = (int)s;
+    u.i1 = u.i0 + ((u.i0 < n_in - 1) ? 1 : 0);
+    u.w1 = s - (float)u.i0;
+    u.w0 = 1.0f - u.w1;
+    return u;
+}
+
+__global__ void __launch_bounds__(256) act_upcat_kernel(const float* __restrict__ low, const float* __restrict__ lsc, const float* __restrict__ lsh,
+                                                        const float* __restrict__ skip, const float* __restrict__ ssc, const float* __restrict__ ssh,
+                                                        float* __restrict__ out, long long total, int C1, int C2, int H, int W,
+                                                        float ry, float rx) {
+    const int Ho = 2 * H, Wo = 2 * W, Ct = C1 + C2;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % Wo);
+        const int y = (int)((idx / Wo) % Ho);
+        const int c = (int)((idx / ((long long)Wo * Ho)) % Ct);
+        const long long b = idx / ((long long)Wo * Ho * Ct);
+        float v;
+        if (c < C1) {
+            const float sc = __ldg(lsc + c), sh = __ldg(lsh + c);
+            const UpCoord uy = up_coord(y, H, ry), ux = up_coord(x, W, rx);
+            const float* p = low + ((size_t)b * C1 + c) * H * W;
+            const float v00 = sifnn::act_affine_relu(__ldg(p + (size_t)uy.i0 * W + ux.i0), sc, sh);
+            const float v01 = sifnn::act_affine_relu(__ldg(p + (size_t)uy.i0 * W + ux.i1), sc, sh);
+            const float v10 = sifnn::act_affine_relu(__ldg(p + (size_t)uy.i1 * W + ux.i0), sc, sh);
+            const float v11 = sifnn::act_affine_relu(__ldg(p + (size_t)uy.i1 * W + ux.i1), sc, sh);
+            v = uy.w0 * (ux.w0 * v00 + ux.w1 * v01) + uy.w1 * (ux.w0 * v10 + ux.w1 * v11);
+        } else {
+            const int cs = c - C1;
+            v = sifnn::act_affine_relu(__ldg(skip + ((size_t)b * C2 + cs) * Ho * Wo + (size_t)y * Wo + x), __ldg(ssc + cs), __ldg(ssh + cs));
+        }
+        out[idx] = v;
+    }
+}
+
+// dlow[b][c][i][k] = sum_{y,x} wy(i,y) wx(k,x) dout[b][c][y][x]  (gather form of the adjoint)
+__global__ void __launch_bounds__(256) upcat_bwd_low_kernel(const float* __restrict__ dout, float* __restrict__ dlow, long long total,
+                                                            int C1, int C2, int H, int W, float ry, float rx) {
+    const int Ho = 2 * H, Wo = 2 * W, Ct = C1 + C2;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % W);
+        const int i = (int)((idx / W) % H);
+        const int c = (int)((idx / ((long long)W * H)) % C1);
+        const long long b = idx / ((long long)W * H * C1);
+        const float* g = dout + ((size_t)b * Ct + c) * Ho * Wo;
+        float wyv[6], wxv[6];
+        int ys[6], xs[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            const int y = 2 * i - 2 + t;
+            ys[t] = y;
+            float wgt = 0.f;
+            if (y >= 0 && y < Ho) {
+                const UpCoord u = up_coord(y, H, ry);
+                if (u.i0 == i) wgt += u.w0;
+                if (u.i1 == i) wgt += u.w1;
+            }
+            wyv[t] = wgt;
+            const int x = 2 * k - 2 + t;
+            xs[t] = x;
+            wgt = 0.f;
+            if (x >= 0 && x < Wo) {
+                const UpCoord u = up_coord(x, W, rx);
+                if (u.i0 == k) wgt += u.w0;
+                if (u.i1 == k) wgt += u.w1;
+            }
+            wxv[t] = wgt;
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            if (wyv[t] != 0.f) {
+                float row = 0.f;
+#pragma unroll
+                for (int u = 0; u < 6; ++u)
+                    if (wxv[u] != 0.f) row = fmaf(wxv[u], __ldg(g + (size_t)ys[t] * Wo + xs[u]), row);
+                acc = fmaf(wyv[t], row, acc);
+            }
+        }
+        dlow[idx] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) upcat_bwd_skip_kernel(const float* __restrict__ dout, float* __restrict__ dskip, long long total4,
+                                                             int C1, int C2, int HWo4) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
+        const long long per_img = (long long)C2 * HWo4;
+        const long long b = idx / per_img;
+        const long long r = idx - b * per_img;
+        reinterpret_cast<float4*>(dskip)[idx] = __ldg(reinterpret_cast<const float4*>(dout) + (b * (C1 + C2) + C1) * (long long)HWo4 + r);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bicubic x4 (Keys a=-0.75, half-pixel centres, clamped borders == cv2.INTER_CUBIC,
+// utils.py:163-180) fused with the channel concat (train_model_B_gradFTM.py:94)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cubic_coeffs(float t, float* c) {
+    const float A = -0.75f;
+    const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+    c[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+    c[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+    c[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+    c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+__global__ void __launch_bounds__(256) bicubic4_cat_kernel(const float* __restrict__ lst, const float* __restrict__ ndvi, float* __restrict__ xout,
+                                                           long long total, int h, int w) {
+    const int H = 4 * h, W = 4 * w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % W);
+        const int y = (int)((idx / W) % H);
+        const long long b = idx / ((long long)W * H);
+        const float sy = ((float)y + 0.5f) * 0.25f - 0.5f, sx = ((float)x + 0.5f) * 0.25f - 0.5f;
+        const float fy = floorf(sy), fx = floorf(sx);
+        float cy[4], cx[4];
+        cubic_coeffs(sy - fy, cy);
+        cubic_coeffs(sx - fx, cx);
+        const int iy = (int)fy, ix = (int)fx;
+        const float* p = lst + (size_t)b * h * w;
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int yy = min(max(iy - 1 + a, 0), h - 1);
+            float row = 0.f;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int xx = min(max(ix - 1 + d, 0), w - 1);
+                row = fmaf(cx[d], __ldg(p + (size_t)yy * w + xx), row);
+            }
+            acc = fmaf(cy[a], row, acc);
+        }
+        const size_t o = (size_t)b * 2 * H * W + (size_t)y * W + x;
+        xout[o] = acc;
+        xout[o + (size_t)H * W] = __ldg(ndvi + (size_t)b * H * W + (size_t)y * W + x);
+    }
+}
+
+}  // namespace
+
+// ==========================================================================================
+extern "C" int sifnn_bn_train_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                                       float* running_var, float* scale, float* shift, float* save_mean, float* save_invstd,
+                                       int C, double n, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(stats && gamma && beta && scale && shift && save_mean && save_invstd && C > 0 && n > 0, "bn_train_finalize: bad arguments");
+    SIFNN_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_train_finalize: running buffers must both be set or both NULL");
+    bn_train_finalize_kernel<<<(C + 63) / 64, 64, 0, sifnn::as_stream(stream)>>>(stats, gamma, beta, running_mean, running_var, scale, shift, save_mean, save_invstd, C, n);
+    return sifnn::check_launch("bn_train_finalize_kernel");
+}
+
+extern "C" int sifnn_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                                    float* scale, float* shift, int C, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && C > 0, "bn_eval_affine: bad arguments");
+    bn_eval_affine_kernel<<<(C + 63) / 64, 64, 0, sifnn::as_stream(stream)>>>(gamma, beta, running_mean, running_var, scale, shift, C);
+    return sifnn::check_launch("bn_eval_affine_kernel");
+}
+
+static int bn_bwd_chunks(int B, int C, int HW) {
+    const int n4 = HW / 4;
+    long long want = (long long)sifnn::num_sms() * 8 / ((long long)B * C) + 1;
+    long long maxc = (n4 + 255) / 256;
+    if (want > maxc) want = maxc;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+extern "C" int sifnn_bn_relu_bwd_reduce(const float* dY, const float* raw, const float* scale, const float* shift,
+                                        const float* save_mean, const float* save_invstd, double* sums, int B, int C, int HW,
+                                        sifnn_stream_t stream) {
+    SIFNN_REQUIRE(dY && raw && scale && shift && save_mean && save_invstd && sums, "bn_relu_bwd_reduce: null pointer");
+    SIFNN_REQUIRE(B > 0 && C > 0 && HW > 0 && HW % 4 == 0 && B <= 65535 && C <= 65535, "bn_relu_bwd_reduce: bad shape (HW must be a multiple of 4)");
+    dim3 grid(bn_bwd_chunks(B, C, HW), C, B);
+    bn_relu_bwd_reduce_kernel<<<grid, 256, 0, sifnn::as_stream(stream)>>>(dY, raw, scale, shift, save_mean, save_invstd, sums, C, HW);
+    return sifnn::check_launch("bn_relu_bwd_reduce_kernel");
+}
+
+extern "C" int sifnn_bn_relu_bwd_apply(const float* dY, const float* raw, const float* scale, const float* shift,
+                                       const float* save_mean, const float* save_invstd, const float* gamma, const double* sums,
+                                       float* dx, float* dgamma, float* dbeta, int B, int C, int HW, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(dY && raw && scale && shift && save_mean && save_invstd && gamma && sums && dx, "bn_relu_bwd_apply: null pointer");
+    SIFNN_REQUIRE(B > 0 && C > 0 && HW > 0 && HW % 4 == 0 && B <= 65535 && C <= 65535, "bn_relu_bwd_apply: bad shape (HW must be a multiple of 4)");
+    dim3 grid(bn_bwd_chunks(B, C, HW), C, B);
+    bn_relu_bwd_apply_kernel<<<grid, 256, 0, sifnn::as_stream(stream)>>>(dY, raw, scale, shift, save_mean, save_invstd, gamma, sums, dx, dgamma, dbeta, C, HW,
+                                                                           1.0 / ((double)B * HW));
+    return sifnn::check_launch("bn_relu_bwd_apply_kernel");
+}
+
+extern "C" int sifnn_act_avgpool2_fwd(const float* raw, const float* scale, const float* shift, float* out, int B, int C, int H, int W,
+                                      sifnn_stream_t stream) {
+    SIFNN_REQUIRE(raw && scale && shift && out, "act_avgpool2_fwd: null pointer");
+    SIFNN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 4 == 0, "act_avgpool2_fwd: need even H and W %% 4 == 0");
+    const long long total = (long long)B * C * (H / 2) * (W / 4);
+    act_avgpool2_kernel<<<grid_for(total, 256), 256, 0, sifnn::as_stream(stream)>>>(raw, scale, shift, out, total, C, H, W);
+    return sifnn::check_launch("act_avgpool2_kernel");
+}
+
+extern "C" int sifnn_avgpool2_bwd(const float* dout, float* din, int accumulate, int B, int C, int H, int W, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(dout && din, "avgpool2_bwd: null pointer");
+    SIFNN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 4 == 0, "avgpool2_bwd: need even H and W %% 4 == 0");
+    const long long total = (long long)B * C * (H / 2) * (W / 4);
+    avgpool2_bwd_kernel<<<grid_for(total, 256), 256, 0, sifnn::as_stream(stream)>>>(dout, din, total, H, W, accumulate ? 1 : 0);
+    return sifnn::check_launch("avgpool2_bwd_kernel");
+}
+
+extern "C" int sifnn_act_residual_fwd(const float* x, const float* raw, const float* scale, const float* shift, float* out, int B, int C,
+                                      int HW, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(x && raw && scale && shift && out, "act_residual_fwd: null pointer");
+    SIFNN_REQUIRE(B > 0 && C > 0 && HW > 0 && HW % 4 == 0, "act_residual_fwd: HW must be a multiple of 4");
+    const long long total4 = (long long)B * C * (HW / 4);
+    act_residual_kernel<<<grid_for(total4, 256), 256, 0, sifnn::as_stream(stream)>>>(x, raw, scale, shift, out, total4, C, HW / 4);
+    return sifnn::check_launch("act_residual_kernel");
+}
+
+static inline float up_ratio(int n_in) { return n_in > 1 ? (float)(n_in - 1) / (float)(2 * n_in - 1) : 0.f; }
+
+extern "C" int sifnn_act_upcat_fwd(const float* low, const float* low_scale, const float* low_shift, const float* skip,
+                                   const float* skip_scale, const float* skip_shift, float* out, int B, int C1, int C2, int H, int W,
+                                   sifnn_stream_t stream) {
+    SIFNN_REQUIRE(low && low_scale && low_shift && skip && skip_scale && skip_shift && out, "act_upcat_fwd: null pointer");
+    SIFNN_REQUIRE(B > 0 && C1 > 0 && C2 > 0 && H > 0 && W > 0, "act_upcat_fwd: bad shape");
+    const long long total = (long long)B * (C1 + C2) * 4 * H * W;
+    act_upcat_kernel<<<grid_for(total, 256), 256, 0, sifnn::as_stream(stream)>>>(low, low_scale, low_shift, skip, skip_scale, skip_shift, out, total, C1, C2, H, W,
+                                                                                   up_ratio(H), up_ratio(W));
+    return sifnn::check_launch("act_upcat_kernel");
+}
+
+extern "C" int sifnn_upcat_bwd(const float* dout, float* dlow, float* dskip, int B, int C1, int C2, int H, int W, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(dout && dlow && dskip, "upcat_bwd: null pointer");
+    SIFNN_REQUIRE(B > 0 && C1 > 0 && C2 > 0 && H > 0 && W > 0 && (H * W) % 1 == 0, "upcat_bwd: bad shape");
+    cudaStream_t st = sifnn::as_stream(stream);
+    const long long total = (long long)B * C1 * H * W;
+    upcat_bwd_low_kernel<<<grid_for(total, 256), 256, 0, st>>>(dout, dlow, total, C1, C2, H, W, up_ratio(H), up_ratio(W));
+    SIFNN_TRY(sifnn::check_launch("upcat_bwd_low_kernel"));
+    const int HWo4 = H * W;  // (2H*2W)/4
+    const long long total4 = (long long)B * C2 * HWo4;
+    upcat_bwd_skip_kernel<<<grid_for(total4, 256), 256, 0, st>>>(dout, dskip, total4, C1, C2, HWo4);
+    return sifnn::check_launch("upcat_bwd_skip_kernel");
+}
+
+extern "C" int sifnn_bicubic4_cat(const float* lst, const float* ndvi, float* x, int B, int h, int w, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(lst && ndvi && x && B > 0 && h > 0 && w > 0, "bicubic4_cat: bad arguments");
+    const long long total = (long long)B * 16 * h * w;
+    bicubic4_cat_kernel<<<grid_for(total, 256), 256, 0, sifnn::as_stream(stream)>>>(lst, ndvi, x, total, h, w);
+    return sifnn::check_launch("bicubic4_cat_kernel");
+}

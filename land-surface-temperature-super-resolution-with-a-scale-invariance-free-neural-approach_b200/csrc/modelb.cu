@@ -1,0 +1,303 @@
+// ModelB_2.forward (model.py:608-645) and its backward as one host-side launch plan over
+// the kernels of this library.  Every convolution stores its RAW (pre-BatchNorm) output;
+// BatchNorm + ReLU are applied by whoever consumes it (the next convolution's load stage,
+// the pooling / residual / up-sample kernels), so no activation tensor is materialised
+// twice and the backward pass recomputes activations from the same raw tensors.
+//
+// The caller owns the workspace; this file only carves it up.
+#include "common.cuh"
+
+#include <cstring>
+
+namespace {
+
+struct ConvDesc { int cin, cout, level; };
+
+struct Net {
+    ConvDesc conv[SIFNN_MODELB_NCONV];
+    int64_t w_off[SIFNN_MODELB_NCONV];
+    int64_t gamma_off[SIFNN_MODELB_NBN], beta_off[SIFNN_MODELB_NBN], bn_off[SIFNN_MODELB_NBN];
+    int64_t bias_off, n_params, bn_total;
+    int d[4];
+    bool ok;
+};
+
+Net build_net(const sifnn_modelb_cfg* cfg) {
+    Net n{};
+    n.ok = false;
+    if (!cfg) return n;
+    const int in = cfg->in_channels, d0 = cfg->down[0], d1 = cfg->down[1], d2 = cfg->down[2], d3 = cfg->down[3];
+    if (in <= 0 || d0 <= 0 || d1 != 2 * d0 || d2 != 2 * d1 || d3 != 2 * d2) return n;  // cat([up, skip]) must match UpBlock's in_channels
+    const int half = d3 / 2;
+    const ConvDesc t[SIFNN_MODELB_NCONV] = {
+        {in, d0, 0}, {d0, d0, 0},                       // inbloc
+        {d0, d0, 1}, {d0, d0, 1}, {d0, d1, 1},          // db1
+        {d1, d1, 2}, {d1, d1, 2}, {d1, d2, 2},          // db2
+        {d2, d2, 3}, {d2, d2, 3}, {d2, half, 3},        // db3
+        {d3, d3 / 2, 2}, {d3 / 2, d2 / 2, 2},           // ub1
+        {d2, d2 / 2, 1}, {d2 / 2, d1 / 2, 1},           // ub2
+        {d1, d1 / 2, 0}, {d1 / 2, d0, 0},               // ub3
+        {d0, 1, 0},                                     // outlay
+    };
+    int64_t off = 0, boff = 0;
+    for (int i = 0; i < SIFNN_MODELB_NCONV; ++i) {
+        n.conv[i] = t[i];
+        n.w_off[i] = off;
+        off += (int64_t)t[i].cout * t[i].cin * 9;
+        if (i < SIFNN_MODELB_NBN) {
+            n.gamma_off[i] = off; off += t[i].cout;
+            n.beta_off[i] = off; off += t[i].cout;
+            n.bn_off[i] = boff; boff += t[i].cout;
+        } else {
+            n.bias_off = off; off += t[i].cout;
+        }
+    }
+    n.n_params = off;
+    n.bn_total = boff;
+    n.d[0] = d0; n.d[1] = d1; n.d[2] = d2; n.d[3] = d3;
+    n.ok = true;
+    return n;
+}
+
+struct Carver {
+    char* base;
+    size_t off;
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct Workspace {
+    float* raw[SIFNN_MODELB_NBN];
+    float* P[3];
+    float* R[3];
+    float* U[3];
+    float *scale, *shift, *mean, *invstd;  // bn_total each
+    double* stats;                          // 2 * bn_total (layer i at 2*bn_off[i])
+    double* bsums;                          // 2 * bn_total
+    // training only
+    float* g[SIFNN_MODELB_NBN];
+    float* gR[3];
+    float* gU[3];
+    void* wgrad_ws;
+    size_t bytes;
+};
+
+Workspace carve(const Net& n, void* base, int B, int H, int W, int train) {
+    Workspace w{};
+    Carver c{static_cast<char*>(base), 0};
+    const size_t hw[4] = {(size_t)H * W, (size_t)H * W / 4, (size_t)H * W / 16, (size_t)H * W / 64};
+    for (int i = 0; i < SIFNN_MODELB_NBN; ++i) w.raw[i] = c.take<float>((size_t)B * n.conv[i].cout * hw[n.conv[i].level]);
+    for (int k = 0; k < 3; ++k) {
+        const size_t sz = (size_t)B * n.d[k] * hw[k + 1];
+        w.P[k] = c.take<float>(sz);
+        w.R[k] = c.take<float>(sz);
+    }
+    // U1 (d3 @ L2), U2 (d2 @ L1), U3 (d1 @ L0)
+    for (int k = 0; k < 3; ++k) w.U[k] = c.take<float>((size_t)B * n.d[3 - k] * hw[2 - k]);
+    w.scale = c.take<float>(n.bn_total);
+    w.shift = c.take<float>(n.bn_total);
+    w.mean = c.take<float>(n.bn_total);
+    w.invstd = c.take<float>(n.bn_total);
+    w.stats = c.take<double>(2 * n.bn_total);
+    w.bsums = c.take<double>(2 * n.bn_total);
+    if (train) {
+        for (int i = 0; i < SIFNN_MODELB_NBN; ++i) w.g[i] = c.take<float>((size_t)B * n.conv[i].cout * hw[n.conv[i].level]);
+        for (int k = 0; k < 3; ++k) w.gR[k] = c.take<float>((size_t)B * n.d[k] * hw[k + 1]);
+        for (int k = 0; k < 3; ++k) w.gU[k] = c.take<float>((size_t)B * n.d[3 - k] * hw[2 - k]);
+        size_t mx = 0;
+        for (int i = 0; i < SIFNN_MODELB_NCONV; ++i) {
+            const int s = n.conv[i].level;
+            const size_t b = sifnn_conv3x3_wgrad_workspace(B, n.conv[i].cin, n.conv[i].cout, H >> s, W >> s);
+            if (b > mx) mx = b;
+        }
+        w.wgrad_ws = c.take<char>(mx);
+    }
+    c.off = (c.off + 255) & ~(size_t)255;
+    w.bytes = c.off;
+    return w;
+}
+
+struct EvalTable {
+    int64_t gamma_off[SIFNN_MODELB_NBN], beta_off[SIFNN_MODELB_NBN], bn_off[SIFNN_MODELB_NBN + 1];
+};
+
+__global__ void bn_eval_affine_all_kernel(const float* __restrict__ params, const float* __restrict__ rm, const float* __restrict__ rv,
+                                          float* scale, float* shift, const EvalTable t, int total) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= total) return;
+    int l = 0;
+#pragma unroll 1
+    while (l + 1 < SIFNN_MODELB_NBN && j >= t.bn_off[l + 1]) ++l;
+    const int c = j - (int)t.bn_off[l];
+    const float invstd = 1.0f / sqrtf(rv[j] + 1e-5f);
+    const float sc = params[t.gamma_off[l] + c] * invstd;
+    scale[j] = sc;
+    shift[j] = fmaf(-rm[j], sc, params[t.beta_off[l] + c]);
+}
+
+bool shape_ok(int B, int H, int W) { return B > 0 && B <= 65535 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0; }
+
+}  // namespace
+
+extern "C" int64_t sifnn_modelb_param_layout(const sifnn_modelb_cfg* cfg, int64_t* w_off, int64_t* gamma_off, int64_t* beta_off,
+                                             int64_t* bias_off, int64_t* bn_off, int64_t* bn_total) {
+    const Net n = build_net(cfg);
+    if (!n.ok) { sifnn::set_error("modelb: unsupported configuration (need down[k+1] == 2*down[k])"); return -1; }
+    if (w_off) memcpy(w_off, n.w_off, sizeof(n.w_off));
+    if (gamma_off) memcpy(gamma_off, n.gamma_off, sizeof(n.gamma_off));
+    if (beta_off) memcpy(beta_off, n.beta_off, sizeof(n.beta_off));
+    if (bias_off) *bias_off = n.bias_off;
+    if (bn_off) memcpy(bn_off, n.bn_off, sizeof(n.bn_off));
+    if (bn_total) *bn_total = n.bn_total;
+    return n.n_params;
+}
+
+extern "C" int64_t sifnn_modelb_decoder_offset(const sifnn_modelb_cfg* cfg) {
+    const Net n = build_net(cfg);
+    return n.ok ? n.w_off[11] : -1;
+}
+
+extern "C" size_t sifnn_modelb_workspace_bytes(const sifnn_modelb_cfg* cfg, int B, int H, int W, int train) {
+    const Net n = build_net(cfg);
+    if (!n.ok || !shape_ok(B, H, W)) return 0;
+    return carve(n, nullptr, B, H, W, train).bytes;
+}
+
+extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* params, float* running_mean, float* running_var,
+                                    const float* x, float* y, void* workspace, int B, int H, int W, int train, sifnn_stream_t stream) {
+    const Net n = build_net(cfg);
+    SIFNN_REQUIRE(n.ok, "modelb_forward: unsupported configuration (need down[k+1] == 2*down[k])");
+    SIFNN_REQUIRE(params && running_mean && running_var && x && y && workspace, "modelb_forward: null pointer");
+    SIFNN_REQUIRE(shape_ok(B, H, W), "modelb_forward: need H, W multiples of 8 and 1 <= B <= 65535 (got B=%d H=%d W=%d)", B, H, W);
+    const Workspace w = carve(n, workspace, B, H, W, train);
+    cudaStream_t st = sifnn::as_stream(stream);
+    const int hs[4] = {H, H / 2, H / 4, H / 8}, ws[4] = {W, W / 2, W / 4, W / 8};
+
+    if (train) {
+        SIFNN_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(double) * 2 * n.bn_total, st));
+    } else {
+        EvalTable t{};
+        for (int i = 0; i < SIFNN_MODELB_NBN; ++i) { t.gamma_off[i] = n.gamma_off[i]; t.beta_off[i] = n.beta_off[i]; t.bn_off[i] = n.bn_off[i]; }
+        t.bn_off[SIFNN_MODELB_NBN] = n.bn_total;
+        bn_eval_affine_all_kernel<<<((int)n.bn_total + 127) / 128, 128, 0, st>>>(params, running_mean, running_var, w.scale, w.shift, t, (int)n.bn_total);
+        SIFNN_TRY(sifnn::check_launch("bn_eval_affine_all_kernel"));
+    }
+
+    // conv i reading `in` (plain if aff < 0, else BatchNorm+ReLU of layer `aff` applied on load)
+    auto conv = [&](int i, const float* in, int aff, float* out) -> int {
+        const ConvDesc& c = n.conv[i];
+        const int l = c.level;
+        const bool bn = i < SIFNN_MODELB_NBN;
+        SIFNN_TRY(sifnn_conv3x3_fwd(in, aff >= 0 ? w.scale + n.bn_off[aff] : nullptr, aff >= 0 ? w.shift + n.bn_off[aff] : nullptr,
+                                    params + n.w_off[i], bn ? nullptr : params + n.bias_off, out,
+                                    (bn && train) ? w.stats + 2 * n.bn_off[i] : nullptr, B, c.cin, c.cout, hs[l], ws[l], stream));
+        if (bn && train) {
+            const int64_t o = n.bn_off[i];
+            SIFNN_TRY(sifnn_bn_train_finalize(w.stats + 2 * o, params + n.gamma_off[i], params + n.beta_off[i], running_mean + o, running_var + o,
+                                              w.scale + o, w.shift + o, w.mean + o, w.invstd + o, c.cout, (double)B * hs[l] * ws[l], stream));
+        }
+        return 0;
+    };
+    auto sc = [&](int i) { return w.scale + n.bn_off[i]; };
+    auto sh = [&](int i) { return w.shift + n.bn_off[i]; };
+
+    SIFNN_TRY(conv(0, x, -1, w.raw[0]));
+    SIFNN_TRY(conv(1, w.raw[0], 0, w.raw[1]));
+    for (int k = 0; k < 3; ++k) {  // db1..db3
+        const int src = 3 * k + 1, c0 = 3 * k + 2, c1 = 3 * k + 3, last = 3 * k + 4;
+        const int C = n.d[k];
+        SIFNN_TRY(sifnn_act_avgpool2_fwd(w.raw[src], sc(src), sh(src), w.P[k], B, C, hs[k], ws[k], stream));
+        SIFNN_TRY(conv(c0, w.P[k], -1, w.raw[c0]));
+        SIFNN_TRY(conv(c1, w.raw[c0], c0, w.raw[c1]));
+        SIFNN_TRY(sifnn_act_residual_fwd(w.P[k], w.raw[c1], sc(c1), sh(c1), w.R[k], B, C, hs[k + 1] * ws[k + 1], stream));
+        SIFNN_TRY(conv(last, w.R[k], -1, w.raw[last]));
+    }
+    for (int k = 0; k < 3; ++k) {  // ub1..ub3
+        const int low = (k == 0) ? 10 : 10 + 2 * k, skip = 7 - 3 * k, c0 = 11 + 2 * k, c1 = 12 + 2 * k;
+        const int ll = 3 - k;  // level of the low-resolution input
+        SIFNN_TRY(sifnn_act_upcat_fwd(w.raw[low], sc(low), sh(low), w.raw[skip], sc(skip), sh(skip), w.U[k], B, n.conv[low].cout,
+                                      n.conv[skip].cout, hs[ll], ws[ll], stream));
+        SIFNN_TRY(conv(c0, w.U[k], -1, w.raw[c0]));
+        SIFNN_TRY(conv(c1, w.raw[c0], c0, w.raw[c1]));
+    }
+    SIFNN_TRY(conv(17, w.raw[16], 16, y));
+    return 0;
+}
+
+extern "C" int sifnn_modelb_backward(const sifnn_modelb_cfg* cfg, const float* params, const float* x, const float* dy, float* grads,
+                                     void* workspace, int B, int H, int W, int phase, sifnn_stream_t stream) {
+    const Net n = build_net(cfg);
+    SIFNN_REQUIRE(n.ok, "modelb_backward: unsupported configuration");
+    SIFNN_REQUIRE(params && x && dy && grads && workspace, "modelb_backward: null pointer");
+    SIFNN_REQUIRE(shape_ok(B, H, W), "modelb_backward: bad shape B=%d H=%d W=%d", B, H, W);
+    SIFNN_REQUIRE(phase >= 0 && phase <= 2, "modelb_backward: phase must be 0, 1 or 2");
+    const Workspace w = carve(n, workspace, B, H, W, 1);
+    cudaStream_t st = sifnn::as_stream(stream);
+    const int hs[4] = {H, H / 2, H / 4, H / 8}, ws[4] = {W, W / 2, W / 4, W / 8};
+
+    auto sc = [&](int i) { return w.scale + n.bn_off[i]; };
+    auto sh = [&](int i) { return w.shift + n.bn_off[i]; };
+    // gradient of conv i's weights; input = raw[aff] through BN+ReLU, or a plain tensor
+    auto wgrad = [&](int i, const float* in, int aff, const float* g) -> int {
+        const ConvDesc& c = n.conv[i];
+        return sifnn_conv3x3_wgrad(in, aff >= 0 ? sc(aff) : nullptr, aff >= 0 ? sh(aff) : nullptr, g, grads + n.w_off[i],
+                                   i == 17 ? grads + n.bias_off : nullptr, w.wgrad_ws, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
+    };
+    auto dgrad = [&](int i, const float* g, float* dx, int accumulate) -> int {
+        const ConvDesc& c = n.conv[i];
+        return sifnn_conv3x3_dgrad(g, params + n.w_off[i], dx, accumulate, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
+    };
+    // BatchNorm+ReLU backward of layer i: dY (gradient w.r.t. the activated output) -> dx (w.r.t. raw[i])
+    auto bnbwd = [&](int i, const float* dY, float* dx) -> int {
+        const ConvDesc& c = n.conv[i];
+        const int64_t o = n.bn_off[i];
+        const int HW = hs[c.level] * ws[c.level];
+        SIFNN_TRY(sifnn_bn_relu_bwd_reduce(dY, w.raw[i], w.scale + o, w.shift + o, w.mean + o, w.invstd + o, w.bsums + 2 * o, B, c.cout, HW, stream));
+        return sifnn_bn_relu_bwd_apply(dY, w.raw[i], w.scale + o, w.shift + o, w.mean + o, w.invstd + o, params + n.gamma_off[i], w.bsums + 2 * o, dx,
+                                       grads + n.gamma_off[i], grads + n.beta_off[i], B, c.cout, HW, stream);
+    };
+
+    if (phase == 0 || phase == 1) {
+        SIFNN_CUDA(cudaMemsetAsync(w.bsums, 0, sizeof(double) * 2 * n.bn_total, st));
+        SIFNN_TRY(wgrad(17, w.raw[16], 16, dy));
+        SIFNN_TRY(dgrad(17, dy, w.g[16], 0));
+        for (int k = 2; k >= 0; --k) {  // ub3, ub2, ub1
+            const int low = (k == 0) ? 10 : 10 + 2 * k, skip = 7 - 3 * k, c0 = 11 + 2 * k, c1 = 12 + 2 * k;
+            const int ll = 3 - k;
+            SIFNN_TRY(bnbwd(c1, w.g[c1], w.g[c1]));
+            SIFNN_TRY(wgrad(c1, w.raw[c0], c0, w.g[c1]));
+            SIFNN_TRY(dgrad(c1, w.g[c1], w.g[c0], 0));
+            SIFNN_TRY(bnbwd(c0, w.g[c0], w.g[c0]));
+            SIFNN_TRY(wgrad(c0, w.U[k], -1, w.g[c0]));
+            SIFNN_TRY(dgrad(c0, w.g[c0], w.gU[k], 0));
+            SIFNN_TRY(sifnn_upcat_bwd(w.gU[k], w.g[low], w.g[skip], B, n.conv[low].cout, n.conv[skip].cout, hs[ll], ws[ll], stream));
+        }
+    }
+    if (phase == 0 || phase == 2) {
+        for (int k = 2; k >= 0; --k) {  // db3, db2, db1
+            const int src = 3 * k + 1, c0 = 3 * k + 2, c1 = 3 * k + 3, last = 3 * k + 4;
+            const int C = n.d[k];
+            SIFNN_TRY(bnbwd(last, w.g[last], w.g[last]));
+            SIFNN_TRY(wgrad(last, w.R[k], -1, w.g[last]));
+            SIFNN_TRY(dgrad(last, w.g[last], w.gR[k], 0));
+            SIFNN_TRY(bnbwd(c1, w.gR[k], w.g[c1]));           // residual branch; gR[k] stays = dL/dP so far
+            SIFNN_TRY(wgrad(c1, w.raw[c0], c0, w.g[c1]));
+            SIFNN_TRY(dgrad(c1, w.g[c1], w.g[c0], 0));
+            SIFNN_TRY(bnbwd(c0, w.g[c0], w.g[c0]));
+            SIFNN_TRY(wgrad(c0, w.P[k], -1, w.g[c0]));
+            SIFNN_TRY(dgrad(c0, w.g[c0], w.gR[k], 1));          // += : gR[k] is now dL/dP
+            SIFNN_TRY(sifnn_avgpool2_bwd(w.gR[k], w.g[src], 1, B, C, hs[k], ws[k], stream));  // += onto the skip gradient
+        }
+        SIFNN_TRY(bnbwd(1, w.g[1], w.g[1]));
+        SIFNN_TRY(wgrad(1, w.raw[0], 0, w.g[1]));
+        SIFNN_TRY(dgrad(1, w.g[1], w.g[0], 0));
+        SIFNN_TRY(bnbwd(0, w.g[0], w.g[0]));
+        SIFNN_TRY(wgrad(0, x, -1, w.g[0]));
+    }
+    return 0;
+}

@@ -1,0 +1,146 @@
+"""Fused training step: the body of the reference's ``train_step`` loop
+(train_model_B_gradFTM.py:89-121 for SR2, train_model_B_predef_filters.py:101-137 for
+SR1) as five native launches plans -- input stage, forward, loss (+dLoss/dSR), backward,
+Adam -- with no host synchronisation and no autograd bookkeeping.
+
+Data parallelism (one process per GPU, ``torch.distributed`` / NCCL): the batch is
+sharded across ranks; BatchNorm statistics are local to a rank (PyTorch-DDP semantics:
+same result as the reference run on that rank's shard); the flat 282 705-float gradient
+buffer is all-reduced in two buckets -- the decoder half as soon as the decoder
+backward has been queued, overlapping the encoder backward, then the encoder half --
+and every rank applies the identical Adam update with grad_scale = 1/world_size.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import SifnnError
+from .losses import loss_fwd_bwd
+from .model import ModelB_2, bicubic4_cat, _stream
+
+
+class Trainer:
+    def __init__(self, model: ModelB_2, kind: str = "sr2", alpha: float = 0.5, gamma: float = -0.25, lr: float = 1e-4,
+                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, data_parallel: Optional[bool] = None,
+                 overlap_allreduce: bool = True):
+        if kind not in ("sr1", "sr2"):
+            raise SifnnError("kind must be 'sr1' or 'sr2'")
+        self.model, self.kind, self.alpha, self.gamma = model, kind, float(alpha), float(gamma)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        if data_parallel is None:
+            data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.world = dist.get_world_size() if data_parallel else 1
+        self.overlap = overlap_allreduce
+        self._opt = None
+        self._graph = None
+
+    # ------------------------------------------------------------------ state
+    def _opt_state(self, device):
+        st = self.model._ensure_flat(device)
+        if self._opt is None or self._opt["m"].device != device or self._opt["m"].numel() != st["n"]:
+            self._opt = {"m": torch.zeros(st["n"], dtype=torch.float32, device=device),
+                         "v": torch.zeros(st["n"], dtype=torch.float32, device=device),
+                         "t": torch.zeros((), dtype=torch.int64, device=device)}
+        return st, self._opt
+
+    def broadcast_parameters(self, src: int = 0) -> None:
+        """Make every rank start from rank ``src``'s weights and BatchNorm buffers."""
+        if self.world == 1:
+            return
+        dev = next(self.model.parameters()).device
+        st = self.model._ensure_flat(dev)
+        for t in (st["flat"], st["rm"], st["rv"]):
+            dist.broadcast(t, src)
+
+    # ------------------------------------------------------------------ one step
+    def _backward_and_update(self, x, dsr, ws):
+        m = self.model
+        st, opt = self._opt_state(x.device)
+        fgrad, dec = st["fgrad"], st["dec_off"]
+        if self.world > 1 and self.overlap:
+            m._run_backward(x, dsr, ws, phase=1)
+            w1 = dist.all_reduce(fgrad[dec:], async_op=True)      # decoder bucket, overlaps the encoder backward
+            m._run_backward(x, dsr, ws, phase=2)
+            w2 = dist.all_reduce(fgrad[:dec], async_op=True)
+            w1.wait()
+            w2.wait()
+        else:
+            m._run_backward(x, dsr, ws, phase=0)
+            if self.world > 1:
+                dist.all_reduce(fgrad)
+        _lib.call("sifnn_adam_step", st["flat"].data_ptr(), fgrad.data_ptr(), opt["m"].data_ptr(), opt["v"].data_ptr(),
+                  opt["t"].data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world, st["n"], _stream())
+
+    def _step_impl(self, lst, ndvi, lst_up):
+        m = self.model
+        if not m.training:
+            raise SifnnError("Trainer.step needs model.train()")
+        x = bicubic4_cat(lst, ndvi) if lst_up is None else torch.cat((lst_up, ndvi), dim=1)
+        x = m._check_input(x)
+        y, ws, key = m._run_forward(x, train=True, keep=True)
+        losses, dsr = loss_fwd_bwd(self.kind, y, lst, ndvi, self.alpha, self.gamma, want_grad=True)
+        self._backward_and_update(x, dsr, ws)
+        m._ws.give(key, ws)
+        return losses, y
+
+    def step(self, lst: torch.Tensor, ndvi: torch.Tensor, lst_up: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimisation step on this rank's shard.  lst (B,1,h,w), ndvi (B,1,4h,4w) fp32 CUDA
+        (already z-scored, like the reference Dataset delivers them); ``lst_up`` optional -- when
+        omitted the bicubic x4 is done on the device.  Returns a (3,) float64 device tensor
+        (ds_loss, percep_loss, loss) of the local shard WITHOUT synchronising."""
+        return self._step_impl(lst, ndvi, lst_up)[0]
+
+    def step_host(self, lst_pinned: torch.Tensor, ndvi_pinned: torch.Tensor) -> Tuple[float, float, float]:
+        """End-to-end step from (pinned) HOST buffers: H2D copies, step, D2H of the three scalars."""
+        dev = next(self.model.parameters()).device
+        lst = lst_pinned.to(dev, non_blocking=True)
+        ndvi = ndvi_pinned.to(dev, non_blocking=True)
+        losses = self.step(lst, ndvi)
+        ds, pl, loss = losses.cpu().tolist()
+        return ds, pl, loss
+
+    @torch.no_grad()
+    def evaluate(self, lst: torch.Tensor, ndvi: torch.Tensor, lst_up: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The reference's ``test_step`` body (train_model_B_gradFTM.py:181-215): eval-mode forward + losses."""
+        m = self.model
+        was = m.training
+        m.eval()
+        try:
+            x = bicubic4_cat(lst, ndvi) if lst_up is None else torch.cat((lst_up, ndvi), dim=1)
+            y = m(x)
+            losses, _ = loss_fwd_bwd(self.kind, y, lst, ndvi, self.alpha, self.gamma, want_grad=False)
+        finally:
+            m.train(was)
+        return losses
+
+    # ------------------------------------------------------------------ CUDA graph replay (single GPU)
+    def capture(self, lst: torch.Tensor, ndvi: torch.Tensor) -> None:
+        """Capture the whole step into a CUDA graph for shapes like (lst, ndvi); afterwards
+        ``step_graph`` copies new data into the static buffers and replays it."""
+        if self.world > 1:
+            raise SifnnError("graph capture is single-GPU; the data-parallel step runs eagerly around the NCCL calls")
+        self._static_lst, self._static_ndvi = lst.clone(), ndvi.clone()
+        self._opt_state(lst.device)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):  # warm-up: allocations, lazy attribute setup
+                self._step_impl(self._static_lst, self._static_ndvi, None)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._static_losses, _ = self._step_impl(self._static_lst, self._static_ndvi, None)
+        self._graph = g
+
+    def step_graph(self, lst: torch.Tensor, ndvi: torch.Tensor) -> torch.Tensor:
+        if self._graph is None:
+            raise SifnnError("call capture() first")
+        self._static_lst.copy_(lst, non_blocking=True)
+        self._static_ndvi.copy_(ndvi, non_blocking=True)
+        self._graph.replay()
+        return self._static_losses
