@@ -1,0 +1,362 @@
+#!/usr/bin/env python3
+"""Benchmark of the SIF-NN-SR ModelB hot path (BASELINE.json: "ModelB train patches/s (64->256) at
+1/2/4/8 B200; inference Mpix/s vs CPU").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode train_sr1|train_sr2|infer]
+
+A step = one full training step (bicubic input stage, forward, fused loss, backward, Adam) on one batch
+of synthetic z-scored patches of the paper's shape: per GPU 32 x {LST (1,64,64), NDVI (1,256,256)} ->
+(1,256,256) -- BASELINE.json configs[1] at N=1 ("SR1 training step, batch 32, fp32, 1xB200"); for N>1 the
+per-GPU batch stays 32 (weak scaling, data parallel, two-bucket NCCL all-reduce).  Prints ONE JSON line.
+
+--impl reference times the CPU implementation the reference would run (PyTorch CPU ops through the oracle
+port -- the reference is pure Python/PyTorch and cannot travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+PATCH_MPIX = 256 * 256 / 1e6
+FWD_GFLOP, STEP_GFLOP = 3.605, 10.78  # per patch, SURVEY section 8d
+HYPER = {"train_sr1": ("sr1", 0.99, -0.5, 1e-3), "train_sr2": ("sr2", 0.5, -0.25, 1e-4)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return p.get("hbm_gbs", 6650.0), p.get("bf16_tflops", 1590.0), "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_batches(n_batches, batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(batch, 1, 64, 64, generator=g), torch.randn(batch, 1, 256, 256, generator=g)) for _ in range(n_batches)]
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the CPU path the reference would run
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import sifnn_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    mode = args.mode
+    if mode == "infer":
+        sd = O.init_state_dict(0)
+        bs = 1
+        x = torch.randn(bs, 2, 256, 256, generator=torch.Generator().manual_seed(1234))
+
+        def step():
+            with torch.inference_mode():
+                O.forward(sd, x, train=False)
+        per_step, unit, metric = bs * PATCH_MPIX, "Mpix/s", "ModelB inference Mpix/s"
+        sample = "eval forward of 1 synthetic patch per step (batch 1, like predict.py)"
+    else:
+        kind, alpha, gamma, lr = HYPER[mode]
+        bs = args.ref_batch
+        tr = O.Trainer(O.init_state_dict(0), kind, alpha, gamma, lr)
+        lst, up, ndvi = O.synthetic_batch(bs)
+
+        def step():
+            tr.step(lst, up, ndvi)
+        per_step, unit, metric = bs, "patches/s", f"ModelB {kind.upper()} train patches/s"
+        sample = f"{kind.upper()} train step on {bs} of the 32 patches per step (bounded CPU sample)"
+    for _ in range(min(args.warmup, 1) if args.warmup else 0):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = per_step * args.steps / dt
+    out = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(mode, 32), "reference_path": "PyTorch CPU fp32 (oracle port of model.py + loss helpers)"},
+           "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def workload_name(mode, batch):
+    if mode == "infer":
+        return f"ModelB eval forward, batch {batch} synthetic 64x64 LST + 256x256 NDVI -> 256x256, fp32"
+    return f"ModelB SIF-NN-{HYPER[mode][0].upper()} training step, batch {batch}/GPU synthetic patches (64->256), fp32"
+
+
+# --------------------------------------------------------------------------------------------------
+# per-kernel roofline (measured live, CUDA events on the launch stream)
+# --------------------------------------------------------------------------------------------------
+def kernel_rooflines(batch, fp32_peak):
+    """Times every convolution kernel class on the workload's own layer shapes through the per-op C-ABI."""
+    from sifnn_b200 import ops
+    layers = [(2, 16, 256), (16, 16, 256), (16, 16, 128), (16, 16, 128), (16, 32, 128), (32, 32, 64), (32, 32, 64), (32, 64, 64),
+              (64, 64, 32), (64, 64, 32), (64, 64, 32), (128, 64, 64), (64, 32, 64), (64, 32, 128), (32, 16, 128), (32, 16, 256),
+              (16, 16, 256), (16, 1, 256)]
+    dev = "cuda"
+
+    def timed(fn, reps=3):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    res = {"conv3x3_fwd": [0.0, 0.0, 0], "conv3x3_dgrad": [0.0, 0.0, 0], "conv3x3_wgrad": [0.0, 0.0, 0]}
+    for i, (ci, co, hw) in enumerate(layers):
+        x = torch.randn(batch, ci, hw, hw, device=dev)
+        dy = torch.randn(batch, co, hw, hw, device=dev)
+        w = torch.randn(co, ci, 3, 3, device=dev) * 0.1
+        fl = 2.0 * batch * ci * co * 9 * hw * hw
+        t = timed(lambda: ops.conv3x3_fwd(x, w))
+        res["conv3x3_fwd"][0] += t; res["conv3x3_fwd"][1] += fl; res["conv3x3_fwd"][2] += 1
+        if i > 0:
+            t = timed(lambda: ops.conv3x3_dgrad(dy, w))
+            res["conv3x3_dgrad"][0] += t; res["conv3x3_dgrad"][1] += fl; res["conv3x3_dgrad"][2] += 1
+        t = timed(lambda: ops.conv3x3_wgrad(x, dy, want_bias=(co == 1)))
+        res["conv3x3_wgrad"][0] += t; res["conv3x3_wgrad"][1] += fl; res["conv3x3_wgrad"][2] += 1
+        del x, dy, w
+    out = []
+    for name, (t, fl, n) in res.items():
+        out.append({"kernel": name, "launches_per_step": n, "ms_per_step": t * 1e3, "achieved": fl / t / 1e12, "unit": "TFLOP/s",
+                    "peak": fp32_peak, "frac": fl / t / 1e12 / fp32_peak})
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import sifnn_b200
+    import model as model_mod
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a GPU: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    lib = sifnn_b200.load()
+    torch.manual_seed(0)
+    m = model_mod.ModelB_2(in_channels=2, downchannels=[16, 32, 64, 128], padding_mode="replicate", activation="ReLU",
+                           bilinear=1, n_bridge_blocks=1).to(dev)
+    B = args.batch
+    mode = args.mode
+    nb = 24 if mode != "infer" else 8  # distinct input batches rotated through: 24 x 8.9 MB = 214 MB > 126 MB L2
+    host = [(l.pin_memory(), n.pin_memory()) for l, n in make_batches(nb, B, 1234 + rank)]
+    devb = [(l.to(dev), n.to(dev)) for l, n in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if mode == "infer":
+        m.eval()
+        unit, per_step, metric = "Mpix/s", B * PATCH_MPIX * n_gpus, "ModelB inference Mpix/s"
+
+        def step(i):
+            with torch.inference_mode():
+                return m.forward_from_lowres(*devb[i % nb])
+
+        def step_host(i):
+            l, n = host[i % nb]
+            with torch.inference_mode():
+                y = m.forward_from_lowres(l.to(dev, non_blocking=True), n.to(dev, non_blocking=True))
+            return y.cpu()
+        h2d, d2h = B * (64 * 64 + 256 * 256) * 4, B * 256 * 256 * 4
+        flop_per_step = FWD_GFLOP * 1e9 * B
+    else:
+        kind, alpha, gamma, lr = HYPER[mode]
+        m.train()
+        tr = sifnn_b200.Trainer(m, kind, alpha, gamma, lr)
+        tr.broadcast_parameters(0)
+        unit, per_step, metric = "patches/s", B * n_gpus, f"ModelB {kind.upper()} train patches/s"
+
+        def step(i):
+            return tr.step(*devb[i % nb])
+
+        def step_host(i):
+            return tr.step_host(*host[i % nb])
+        h2d, d2h = B * (64 * 64 + 256 * 256) * 4, 3 * 8
+        flop_per_step = STEP_GFLOP * 1e9 * B
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    launches0 = lib.sifnn_launch_count()
+    with ClockSampler(local) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+    launches = lib.sifnn_launch_count() - launches0
+    # end-to-end: pinned host buffers in, result scalars (or the SR image) out, every step
+    for i in range(2):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+
+    out = None
+    if rank == 0:
+        hbm, bf16, how = peaks()
+        value = per_step * args.steps / (ms * 1e-3)
+        out = {"metric": metric, "value": value, "unit": unit, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic",
+               "config": {"workload": workload_name(mode, B), "batch_per_gpu": B, "global_batch": B * n_gpus,
+                          "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single", "batchnorm": "local (per-rank statistics)",
+                          "weights": "random init, seed 0", "l2": f"{nb} distinct input batches rotated + {2.7 * B / 32:.1f} GB of activations per step (> 126 MB L2)"},
+               "e2e": {"value": per_step * args.steps / (e2e_ms * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": int(launches), "clocks": clk.summary(),
+               "achieved_tflops": flop_per_step * n_gpus * args.steps / (ms * 1e-3) / 1e12}
+    if rank == 0 and not args.no_roofline:
+        from sifnn_b200 import ops
+        fp32_peak = ops.fp32_peak_tflops()
+        per_kernel = kernel_rooflines(B, fp32_peak) if mode != "infer" else kernel_rooflines(B, fp32_peak)[:1]
+        top = max(per_kernel, key=lambda r: r["ms_per_step"])
+        out["roofline"] = {"bound": "fp32", "kernel": top["kernel"], "achieved": top["achieved"], "peak": fp32_peak, "unit": "TFLOP/s",
+                           "frac": top["frac"], "traffic": None,
+                           "note": "fp32 SIMT kernel: the roof is this GPU's measured FFMA throughput (sifnn_fp32_peak_kernel, best of 5), not in "
+                                   f"MEASURED_PEAKS.json; tensor roof for a 3x-split fp32-accurate MMA would be {bf16:.0f}/3 TFLOP/s ({how})",
+                           "per_kernel": per_kernel}
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        import sifnn_oracle as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        if mode == "infer":
+            sd = O.init_state_dict(0)
+            x = torch.randn(1, 2, 256, 256)
+            with torch.inference_mode():
+                O.forward(sd, x)
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    O.forward(sd, x)
+                dt = (time.perf_counter() - t0) / 20
+            out["cpu_baseline"] = {"value": PATCH_MPIX / dt, "unit": unit, "cores": cores, "kind": "port",
+                                   "sample": "20 eval forwards of 1 patch (batch 1, like predict.py), after 1 warm-up"}
+        else:
+            kind, alpha, gamma, lr = HYPER[mode]
+            cb = 16
+            ref = O.Trainer(O.init_state_dict(0), kind, alpha, gamma, lr)
+            lst, up, ndvi = O.synthetic_batch(cb)
+            ref.step(lst, up, ndvi)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                ref.step(lst, up, ndvi)
+            dt = (time.perf_counter() - t0) / 2
+            out["cpu_baseline"] = {"value": cb / dt, "unit": unit, "cores": cores, "kind": "port",
+                                   "sample": f"2 {kind.upper()} train steps of {cb} patches (half a batch) after 1 warm-up, torch CPU fp32"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="train_sr1", choices=["train_sr1", "train_sr2", "infer"])
+    ap.add_argument("--batch", type=int, default=32, help="patches per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=8, help="patches per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

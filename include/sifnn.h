@@ -31,6 +31,8 @@ typedef void* sifnn_stream_t; /* cudaStream_t */
 
 int sifnn_version(void);
 const char* sifnn_last_error(void);
+/* number of CUDA kernels this library has launched in this process (monotonic) */
+unsigned long long sifnn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
  * Per-op entry points

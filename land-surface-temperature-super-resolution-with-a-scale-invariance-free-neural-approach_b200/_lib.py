@@ -62,6 +62,7 @@ _d = POINTER(c_double)
 SIGNATURES = {
     "sifnn_version": (c_int, []),
     "sifnn_last_error": (c_char_p, []),
+    "sifnn_launch_count": (ctypes.c_ulonglong, []),
     "sifnn_conv3x3_fwd": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
     "sifnn_conv3x3_dgrad": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
     "sifnn_conv3x3_wgrad_workspace": (c_size_t, [c_int] * 5),

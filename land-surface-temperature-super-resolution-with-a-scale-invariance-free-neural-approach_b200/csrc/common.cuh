@@ -10,6 +10,7 @@ namespace sifnn {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 int num_sms();
+unsigned long long launches();
 
 inline cudaStream_t as_stream(sifnn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -7,6 +7,7 @@
 namespace sifnn {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;  // kernels launched by this library (bench.py reports it)
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -21,8 +22,11 @@ int check_launch(const char* what) {
         set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
         return (int)e;
     }
+    __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED);
     return 0;
 }
+
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int num_sms() {
     static int n = 0;
@@ -37,6 +41,7 @@ int num_sms() {
 
 extern "C" int sifnn_version(void) { return SIFNN_VERSION; }
 extern "C" const char* sifnn_last_error(void) { return sifnn::g_err; }
+extern "C" unsigned long long sifnn_launch_count(void) { return sifnn::launches(); }
 
 namespace {
 // 8 independent FFMA chains per thread, operands in registers: measures the fp32
