@@ -25,6 +25,19 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+// ---- cp.async (LDGSTS): global -> shared without staging registers; src_bytes < size zero-fills the rest ----
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ float act_affine_relu(float x, float sc, float sh) { return fmaxf(fmaf(x, sc, sh), 0.0f); }
 
 }  // namespace sifnn

@@ -197,32 +197,40 @@ __device__ __forceinline__ UpCoord up_coord(int dst, int n_in, float rscale) {
     return u;
 }
 
+// grid = (ceil(Ho*Wo/4 / 256), C1+C2, B); each thread writes 4 consecutive output pixels (one float4)
 __global__ void __launch_bounds__(256) act_upcat_kernel(const float* __restrict__ low, const float* __restrict__ lsc, const float* __restrict__ lsh,
                                                         const float* __restrict__ skip, const float* __restrict__ ssc, const float* __restrict__ ssh,
-                                                        float* __restrict__ out, long long total, int C1, int C2, int H, int W,
-                                                        float ry, float rx) {
-    const int Ho = 2 * H, Wo = 2 * W, Ct = C1 + C2;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % Wo);
-        const int y = (int)((idx / Wo) % Ho);
-        const int c = (int)((idx / ((long long)Wo * Ho)) % Ct);
-        const long long b = idx / ((long long)Wo * Ho * Ct);
-        float v;
-        if (c < C1) {
-            const float sc = __ldg(lsc + c), sh = __ldg(lsh + c);
-            const UpCoord uy = up_coord(y, H, ry), ux = up_coord(x, W, rx);
-            const float* p = low + ((size_t)b * C1 + c) * H * W;
-            const float v00 = sifnn::act_affine_relu(__ldg(p + (size_t)uy.i0 * W + ux.i0), sc, sh);
-            const float v01 = sifnn::act_affine_relu(__ldg(p + (size_t)uy.i0 * W + ux.i1), sc, sh);
-            const float v10 = sifnn::act_affine_relu(__ldg(p + (size_t)uy.i1 * W + ux.i0), sc, sh);
-            const float v11 = sifnn::act_affine_relu(__ldg(p + (size_t)uy.i1 * W + ux.i1), sc, sh);
-            v = uy.w0 * (ux.w0 * v00 + ux.w1 * v01) + uy.w1 * (ux.w0 * v10 + ux.w1 * v11);
-        } else {
-            const int cs = c - C1;
-            v = sifnn::act_affine_relu(__ldg(skip + ((size_t)b * C2 + cs) * Ho * Wo + (size_t)y * Wo + x), __ldg(ssc + cs), __ldg(ssh + cs));
+                                                        float* __restrict__ out, int C1, int C2, int H, int W, float ry, float rx) {
+    const int Ho = 2 * H, Wo = 2 * W, Wq = Wo >> 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Ho * Wq) return;
+    const int y = t / Wq, x = (t - y * Wq) * 4;
+    const int c = blockIdx.y, b = blockIdx.z;
+    float4 v;
+    if (c < C1) {
+        const float sc = __ldg(lsc + c), sh = __ldg(lsh + c);
+        const UpCoord uy = up_coord(y, H, ry);
+        const float* p0 = low + ((size_t)b * C1 + c) * H * W + (size_t)uy.i0 * W;
+        const float* p1 = low + ((size_t)b * C1 + c) * H * W + (size_t)uy.i1 * W;
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const UpCoord ux = up_coord(x + j, W, rx);
+            const float v00 = sifnn::act_affine_relu(__ldg(p0 + ux.i0), sc, sh);
+            const float v01 = sifnn::act_affine_relu(__ldg(p0 + ux.i1), sc, sh);
+            const float v10 = sifnn::act_affine_relu(__ldg(p1 + ux.i0), sc, sh);
+            const float v11 = sifnn::act_affine_relu(__ldg(p1 + ux.i1), sc, sh);
+            r[j] = uy.w0 * (ux.w0 * v00 + ux.w1 * v01) + uy.w1 * (ux.w0 * v10 + ux.w1 * v11);
         }
-        out[idx] = v;
+        v = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+        const int cs = c - C1;
+        const float sc = __ldg(ssc + cs), sh = __ldg(ssh + cs);
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(skip + ((size_t)b * C2 + cs) * Ho * Wo + (size_t)y * Wo + x));
+        v = make_float4(sifnn::act_affine_relu(s4.x, sc, sh), sifnn::act_affine_relu(s4.y, sc, sh),
+                        sifnn::act_affine_relu(s4.z, sc, sh), sifnn::act_affine_relu(s4.w, sc, sh));
     }
+    *reinterpret_cast<float4*>(out + ((size_t)b * (C1 + C2) + c) * Ho * Wo + (size_t)y * Wo + x) = v;
 }
 
 // dlow[b][c][i][k] = sum_{y,x} wy(i,y) wx(k,x) dout[b][c][y][x]  (gather form of the adjoint)
@@ -410,9 +418,10 @@ extern "C" int sifnn_act_upcat_fwd(const float* low, const float* low_scale, con
                                    sifnn_stream_t stream) {
     SIFNN_REQUIRE(low && low_scale && low_shift && skip && skip_scale && skip_shift && out, "act_upcat_fwd: null pointer");
     SIFNN_REQUIRE(B > 0 && C1 > 0 && C2 > 0 && H > 0 && W > 0, "act_upcat_fwd: bad shape");
-    const long long total = (long long)B * (C1 + C2) * 4 * H * W;
-    act_upcat_kernel<<<grid_for(total, 256), 256, 0, sifnn::as_stream(stream)>>>(low, low_scale, low_shift, skip, skip_scale, skip_shift, out, total, C1, C2, H, W,
-                                                                                   up_ratio(H), up_ratio(W));
+    SIFNN_REQUIRE(W % 2 == 0 && B <= 65535 && C1 + C2 <= 65535, "act_upcat_fwd: need even W, B and channels <= 65535");
+    dim3 grid((2 * H * (2 * W / 4) + 255) / 256, C1 + C2, B);
+    act_upcat_kernel<<<grid, 256, 0, sifnn::as_stream(stream)>>>(low, low_scale, low_shift, skip, skip_scale, skip_shift, out, C1, C2, H, W,
+                                                                   up_ratio(H), up_ratio(W));
     return sifnn::check_launch("act_upcat_kernel");
 }
 

@@ -27,7 +27,95 @@ struct WgradArgs {
     float* bias_partial;  // [S][O]
     int B, K, O, H, W;
     int tiles_x, tiles_per_img, total_tiles;
+    int vec_ok;
 };
+
+// cp.async staging of one pixel tile: K_CHUNK input planes with halo (replicate-clamped) and
+// O_CHUNK dy planes (zero-filled outside the image / past the last channel).
+template <int O_CHUNK, int K_CHUNK, int NT>
+__device__ __forceinline__ void wgrad_issue_fill(float* in_s, float* dy_s, const WgradArgs& a, int b, int x0, int y0, int k0, int o0,
+                                                 bool vec_ok, int tid) {
+    constexpr int IN_ROWS = WROWS + 2;
+    constexpr int IN_PLANE = IN_ROWS * IN_STRIDE;
+    constexpr int DY_PLANE = WROWS * 32;
+    const int H = a.H, W = a.W, K = a.K, O = a.O;
+    const size_t plane = (size_t)H * W;
+    if (vec_ok) {
+        for (int idx = tid; idx < K_CHUNK * IN_ROWS * 10; idx += NT) {
+            const int kk = idx / (IN_ROWS * 10);
+            const int rem = idx - kk * (IN_ROWS * 10);
+            const int r = rem / 10, j = rem - r * 10;
+            const bool ok = k0 + kk < K;
+            const int gy = min(max(y0 + r - 1, 0), H - 1);
+            const float* src = a.in + ((size_t)b * K + (ok ? k0 + kk : 0)) * plane + (size_t)gy * W;
+            float* dst = in_s + kk * IN_PLANE + r * IN_STRIDE;
+            if (j < 8) sifnn::cp_async16(dst + IN_X0 + 1 + 4 * j, src + x0 + 4 * j, ok ? 16 : 0);
+            else if (j == 8) sifnn::cp_async4(dst + IN_X0, src + max(x0 - 1, 0), ok ? 4 : 0);
+            else sifnn::cp_async4(dst + IN_X0 + 33, src + min(x0 + 32, W - 1), ok ? 4 : 0);
+        }
+        for (int idx = tid; idx < O_CHUNK * WROWS * 8; idx += NT) {
+            const int oo = idx / (WROWS * 8);
+            const int rem = idx - oo * (WROWS * 8);
+            const int r = rem >> 3, j = rem & 7;
+            const bool ok = (o0 + oo < O) && (y0 + r < H);
+            const float* src = a.dy + ((size_t)b * O + (ok ? o0 + oo : 0)) * plane + (size_t)(ok ? y0 + r : 0) * W + x0 + 4 * j;
+            sifnn::cp_async16(dy_s + oo * DY_PLANE + r * 32 + 4 * j, src, ok ? 16 : 0);
+        }
+    } else {
+        for (int idx = tid; idx < K_CHUNK * IN_ROWS * IN_COLS; idx += NT) {
+            const int kk = idx / (IN_ROWS * IN_COLS);
+            const int rem = idx - kk * (IN_ROWS * IN_COLS);
+            const int r = rem / IN_COLS, c = rem - r * IN_COLS;
+            const bool ok = k0 + kk < K;
+            const int gy = min(max(y0 + r - 1, 0), H - 1);
+            const int gx = min(max(x0 + c - 1, 0), W - 1);
+            sifnn::cp_async4(in_s + kk * IN_PLANE + r * IN_STRIDE + IN_X0 + c,
+                             a.in + ((size_t)b * K + (ok ? k0 + kk : 0)) * plane + (size_t)gy * W + gx, ok ? 4 : 0);
+        }
+        for (int idx = tid; idx < O_CHUNK * DY_PLANE; idx += NT) {
+            const int oo = idx / DY_PLANE;
+            const int rem = idx - oo * DY_PLANE;
+            const int r = rem >> 5, c = rem & 31;
+            const bool ok = (o0 + oo < O) && (y0 + r < H) && (x0 + c < W);
+            sifnn::cp_async4(dy_s + idx, a.dy + (ok ? ((size_t)b * O + o0 + oo) * plane + (size_t)(y0 + r) * W + x0 + c : 0), ok ? 4 : 0);
+        }
+    }
+}
+
+template <int K_CHUNK, int NT>
+__device__ __forceinline__ void wgrad_affine_pass(float* in_s, const float* sc_s, const float* sh_s, int K, int k0, bool vec_ok, int tid) {
+    constexpr int IN_ROWS = WROWS + 2;
+    constexpr int IN_PLANE = IN_ROWS * IN_STRIDE;
+    if (vec_ok) {
+        for (int idx = tid; idx < K_CHUNK * IN_ROWS * 10; idx += NT) {
+            const int kk = idx / (IN_ROWS * 10);
+            const int rem = idx - kk * (IN_ROWS * 10);
+            const int r = rem / 10, j = rem - r * 10;
+            if (k0 + kk >= K) continue;  // zero-filled planes stay zero (they meet zero... any dy, result unused)
+            const float sc = sc_s[kk], sh = sh_s[kk];
+            float* dst = in_s + kk * IN_PLANE + r * IN_STRIDE;
+            if (j < 8) {
+                float4* q = reinterpret_cast<float4*>(dst + IN_X0 + 1 + 4 * j);
+                float4 v = *q;
+                v.x = sifnn::act_affine_relu(v.x, sc, sh); v.y = sifnn::act_affine_relu(v.y, sc, sh);
+                v.z = sifnn::act_affine_relu(v.z, sc, sh); v.w = sifnn::act_affine_relu(v.w, sc, sh);
+                *q = v;
+            } else {
+                float* q = dst + (j == 8 ? IN_X0 : IN_X0 + 33);
+                *q = sifnn::act_affine_relu(*q, sc, sh);
+            }
+        }
+    } else {
+        for (int idx = tid; idx < K_CHUNK * IN_ROWS * IN_COLS; idx += NT) {
+            const int kk = idx / (IN_ROWS * IN_COLS);
+            const int rem = idx - kk * (IN_ROWS * IN_COLS);
+            const int r = rem / IN_COLS, c = rem - r * IN_COLS;
+            if (k0 + kk >= K) continue;
+            float* q = in_s + kk * IN_PLANE + r * IN_STRIDE + IN_X0 + c;
+            *q = sifnn::act_affine_relu(*q, sc_s[kk], sh_s[kk]);
+        }
+    }
+}
 
 template <int OT, int KT, int O_CHUNK, int K_CHUNK, bool AFFINE, bool BIAS>
 __global__ void __launch_bounds__((O_CHUNK / OT) * (K_CHUNK / KT) * 32, 1) wgrad_kernel(const WgradArgs a) {
@@ -37,17 +125,21 @@ __global__ void __launch_bounds__((O_CHUNK / OT) * (K_CHUNK / KT) * 32, 1) wgrad
     constexpr int IN_ROWS = WROWS + 2;
     constexpr int IN_PLANE = IN_ROWS * IN_STRIDE;
     constexpr int DY_PLANE = WROWS * 32;
+    constexpr int STAGE = K_CHUNK * IN_PLANE + O_CHUNK * DY_PLANE;
 
     extern __shared__ __align__(16) float smem[];
-    float* in_s = smem;
-    float* dy_s = smem + K_CHUNK * IN_PLANE;
+    __shared__ float sc_s[K_CHUNK], sh_s[K_CHUNK];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ot = warp % N_OT, kt = warp / N_OT;
     const int s = blockIdx.x, S = gridDim.x;
     const int k0 = blockIdx.y * K_CHUNK, o0 = blockIdx.z * O_CHUNK;
-    const int H = a.H, W = a.W, K = a.K, O = a.O;
-    const size_t plane = (size_t)H * W;
+    const int K = a.K, O = a.O;
+
+    if (AFFINE && tid < K_CHUNK) {
+        sc_s[tid] = (k0 + tid < K) ? __ldg(a.in_scale + k0 + tid) : 0.f;
+        sh_s[tid] = (k0 + tid < K) ? __ldg(a.in_shift + k0 + tid) : 0.f;
+    }
 
     float acc[OT][KT][9];
     float bsum[OT];
@@ -60,34 +152,40 @@ __global__ void __launch_bounds__((O_CHUNK / OT) * (K_CHUNK / KT) * 32, 1) wgrad
             for (int t = 0; t < 9; ++t) acc[j][k][t] = 0.f;
     }
 
-    for (int tile = s; tile < a.total_tiles; tile += S) {
-        const int b = tile / a.tiles_per_img;
+    auto tile_origin = [&](int tile, int& b, int& x0, int& y0) {
+        b = tile / a.tiles_per_img;
         const int t = tile - b * a.tiles_per_img;
         const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
-        const int x0 = tx * 32, y0 = ty * WROWS;
-        __syncthreads();
-        for (int idx = tid; idx < K_CHUNK * IN_ROWS * IN_COLS; idx += NT) {
-            const int kk = idx / (IN_ROWS * IN_COLS);
-            const int rem = idx - kk * (IN_ROWS * IN_COLS);
-            const int r = rem / IN_COLS, c = rem - r * IN_COLS;
-            const int k = k0 + kk;
-            float v = 0.f;
-            if (k < K) {
-                const int gy = min(max(y0 + r - 1, 0), H - 1);
-                const int gx = min(max(x0 + c - 1, 0), W - 1);
-                v = __ldg(a.in + ((size_t)b * K + k) * plane + (size_t)gy * W + gx);
-                if (AFFINE) v = sifnn::act_affine_relu(v, __ldg(a.in_scale + k), __ldg(a.in_shift + k));
-            }
-            in_s[kk * IN_PLANE + r * IN_STRIDE + IN_X0 + c] = v;
+        x0 = tx * 32;
+        y0 = ty * WROWS;
+    };
+
+    int it = 0;
+    if (s < a.total_tiles) {
+        int b, x0, y0;
+        tile_origin(s, b, x0, y0);
+        wgrad_issue_fill<O_CHUNK, K_CHUNK, NT>(smem, smem + K_CHUNK * IN_PLANE, a, b, x0, y0, k0, o0, a.vec_ok && x0 + 32 <= a.W, tid);
+    }
+    sifnn::cp_async_commit();
+    for (int tile = s; tile < a.total_tiles; tile += S, ++it) {
+        float* in_s = smem + (it & 1) * STAGE;
+        float* dy_s = in_s + K_CHUNK * IN_PLANE;
+        int b, x0, y0;
+        tile_origin(tile, b, x0, y0);
+        const bool vec_ok = a.vec_ok && x0 + 32 <= a.W;
+        if (tile + S < a.total_tiles) {
+            int nb, nx0, ny0;
+            tile_origin(tile + S, nb, nx0, ny0);
+            float* nin = smem + ((it + 1) & 1) * STAGE;
+            wgrad_issue_fill<O_CHUNK, K_CHUNK, NT>(nin, nin + K_CHUNK * IN_PLANE, a, nb, nx0, ny0, k0, o0, a.vec_ok && nx0 + 32 <= a.W, tid);
+            sifnn::cp_async_commit();
+            sifnn::cp_async_wait<1>();
+        } else {
+            sifnn::cp_async_wait<0>();
         }
-        for (int idx = tid; idx < O_CHUNK * DY_PLANE; idx += NT) {
-            const int oo = idx / DY_PLANE;
-            const int rem = idx - oo * DY_PLANE;
-            const int r = rem >> 5, c = rem & 31;
-            const int o = o0 + oo, y = y0 + r, x = x0 + c;
-            float v = 0.f;
-            if (o < O && y < H && x < W) v = __ldg(a.dy + ((size_t)b * O + o) * plane + (size_t)y * W + x);
-            dy_s[idx] = v;
+        if (AFFINE) {
+            if (it == 0) __syncthreads();  // sc_s / sh_s
+            wgrad_affine_pass<K_CHUNK, NT>(in_s, sc_s, sh_s, K, k0, vec_ok, tid);
         }
         __syncthreads();
 
@@ -128,6 +226,7 @@ __global__ void __launch_bounds__((O_CHUNK / OT) * (K_CHUNK / KT) * 32, 1) wgrad
                     win[k][1][kx] = win[k][2][kx];
                 }
         }
+        __syncthreads();  // stage may be refilled by the prefetch of the iteration after next
     }
 
 #pragma unroll
@@ -184,7 +283,7 @@ Plan make_plan(int B, int K, int O, int H, int W) {
 template <int OT, int KT, int O_CHUNK, int K_CHUNK, bool BIAS>
 int launch_wgrad(const WgradArgs& a, const Plan& p, bool affine, cudaStream_t st) {
     constexpr int NT = (O_CHUNK / OT) * (K_CHUNK / KT) * 32;
-    constexpr size_t smem = (size_t)(K_CHUNK * (WROWS + 2) * IN_STRIDE + O_CHUNK * WROWS * 32) * sizeof(float);
+    constexpr size_t smem = 2 * (size_t)(K_CHUNK * (WROWS + 2) * IN_STRIDE + O_CHUNK * WROWS * 32) * sizeof(float);  // two stages
     auto k_aff = wgrad_kernel<OT, KT, O_CHUNK, K_CHUNK, true, BIAS>;
     auto k_pln = wgrad_kernel<OT, KT, O_CHUNK, K_CHUNK, false, BIAS>;
     static bool attr_done = false;
@@ -222,6 +321,7 @@ extern "C" int sifnn_conv3x3_wgrad(const float* in, const float* in_scale, const
     a.bias_partial = a.partial + (size_t)p.S * Cout * Cin * 9;
     a.B = B; a.K = Cin; a.O = Cout; a.H = H; a.W = W;
     a.tiles_x = p.tiles_x; a.tiles_per_img = p.tiles_x * p.tiles_y; a.total_tiles = p.total_tiles;
+    a.vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
     const bool affine = in_scale != nullptr;
     if (p.variant == 2) SIFNN_TRY((launch_wgrad<1, 1, 1, 16, true>(a, p, affine, st)));
     else if (p.variant == 1) SIFNN_TRY((launch_wgrad<2, 1, 16, 2, false>(a, p, affine, st)));
