@@ -38,6 +38,22 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// ---- packed fp32 FMA (FFMA2, sm_100+): two IEEE fmas per instruction.  Same FMA-pipe throughput as two scalar
+// FFMAs but half the issue slots, which is what bounds the direct convolutions (tools/ffma2_probe.cu).  ptxas folds
+// a {x, x} pair into a scalar-broadcast operand, so broadcasting costs no instruction.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 __device__ __forceinline__ float act_affine_relu(float x, float sc, float sh) { return fmaxf(fmaf(x, sc, sh), 0.0f); }
 
 }  // namespace sifnn

@@ -41,100 +41,186 @@ struct ConvArgs {
     int vec_ok;  // W % 4 == 0 and 16-byte aligned base: interior columns may be copied 16 B at a time
 };
 
-// Stage one chunk of input channels (with halo) and its weights into shared memory with
-// cp.async.  Vector path (16 B) for the 32 interior columns when the tile lies fully inside
-// the image in x; the two halo columns and the fallback path are 4 B copies.  Zero padding
-// (PAD_ZERO) is produced by the zero-fill form of cp.async (src-size 0).
-template <int IN_ROWS, int CO_T, int PAD>
-__device__ __forceinline__ void conv_issue_fill(float* in_st, float* w_st, const ConvArgs& a, const float* in_b, int c0, int nci,
-                                                int x0, int y0, int o0, bool vec_ok, int tid) {
-    constexpr int IN_PLANE = IN_ROWS * IN_STRIDE;
-    const int H = a.H, W = a.W;
-    const size_t plane = (size_t)H * W;
-    if (vec_ok) {
-        for (int idx = tid; idx < nci * IN_ROWS * 10; idx += 256) {
-            const int ci = idx / (IN_ROWS * 10);
-            const int rem = idx - ci * (IN_ROWS * 10);
-            const int r = rem / 10, j = rem - r * 10;
+// ---- staging (cp.async) -------------------------------------------------------------------
+// Every thread owns a FIXED set of (tile row, column group) slots for the whole kernel, so the
+// index arithmetic (row clamp / zero-fill decision, offsets) is done once per CTA; per chunk a
+// thread just walks its slots over the chunk's channel planes (pointer += plane).  Vector
+// slots copy 16 B of the 32 interior columns, scalar slots copy one halo element.  Zero padding
+// (PAD_ZERO) is the zero-fill form of cp.async (src-size 0).  The generic per-element path is
+// kept for tiles that are not fully inside the image in x, or unaligned tensors.
+template <int IN_ROWS>
+struct FillSlots {
+    static constexpr int NV = IN_ROWS * 8;              // vector slots per channel plane
+    static constexpr int NS = IN_ROWS * 2;              // scalar (halo) slots per channel plane
+    static constexpr int VSL = (NV + 255) / 256;        // vector slots per thread
+    static constexpr int SOFF = (((NV % 256) + 31) / 32 * 32 + NS <= 256) ? ((NV % 256) + 31) / 32 * 32 : 0;
+    int vsrc[VSL], vdst[VSL], vbytes[VSL];              // vdst < 0: slot unused
+    int ssrc, sdst, sbytes;
+};
+
+template <int IN_ROWS, int PAD>
+__device__ __forceinline__ void conv_make_slots(FillSlots<IN_ROWS>& fs, int H, int W, int x0, int y0, int tid) {
+    using FS = FillSlots<IN_ROWS>;
+#pragma unroll
+    for (int s = 0; s < FS::VSL; ++s) {
+        const int pv = tid + 256 * s;
+        fs.vdst[s] = -1; fs.vsrc[s] = 0; fs.vbytes[s] = 0;
+        if (pv < FS::NV) {
+            const int r = pv >> 3, j = pv & 7;
             int gy = y0 + r - 1;
             bool ok = true;
             if (PAD == PAD_REPLICATE) gy = min(max(gy, 0), H - 1);
             else ok = gy >= 0 && gy < H;
-            const float* src = in_b + (size_t)(c0 + ci) * plane + (size_t)(ok ? gy : 0) * W;
-            float* dst = in_st + ci * IN_PLANE + r * IN_STRIDE;
-            if (j < 8) {
-                sifnn::cp_async16(dst + IN_X0 + 1 + 4 * j, src + x0 + 4 * j, ok ? 16 : 0);
-            } else if (j == 8) {
-                int gx = x0 - 1;
-                if (PAD == PAD_REPLICATE) gx = max(gx, 0);
-                else ok = ok && gx >= 0;
-                sifnn::cp_async4(dst + IN_X0, src + (ok ? gx : 0), ok ? 4 : 0);
-            } else {
-                int gx = x0 + TW;
-                if (PAD == PAD_REPLICATE) gx = min(gx, W - 1);
-                else ok = ok && gx < W;
-                sifnn::cp_async4(dst + IN_X0 + 1 + TW, src + (ok ? gx : 0), ok ? 4 : 0);
-            }
-        }
-    } else {
-        constexpr int IN_COLS = TW + 2;
-        for (int idx = tid; idx < nci * IN_ROWS * IN_COLS; idx += 256) {
-            const int ci = idx / (IN_ROWS * IN_COLS);
-            const int rem = idx - ci * (IN_ROWS * IN_COLS);
-            const int r = rem / IN_COLS, c = rem - r * IN_COLS;
-            int gy = y0 + r - 1, gx = x0 + c - 1;
-            bool ok = true;
-            if (PAD == PAD_REPLICATE) {
-                gy = min(max(gy, 0), H - 1);
-                gx = min(max(gx, 0), W - 1);
-            } else {
-                ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-            }
-            sifnn::cp_async4(in_st + ci * IN_PLANE + r * IN_STRIDE + IN_X0 + c,
-                             in_b + (size_t)(c0 + ci) * plane + (ok ? (size_t)gy * W + gx : 0), ok ? 4 : 0);
+            fs.vdst[s] = r * IN_STRIDE + IN_X0 + 1 + 4 * j;
+            fs.vsrc[s] = ok ? gy * W + x0 + 4 * j : 0;
+            fs.vbytes[s] = ok ? 16 : 0;
         }
     }
-    // weights: w_st[ci][tap][o]
-    for (int idx = tid; idx < nci * 9 * CO_T; idx += 256) {
-        const int o = idx % CO_T;
-        const int t = (idx / CO_T) % 9;
-        const int ci = idx / (9 * CO_T);
-        const bool ok = o0 + o < a.O;
-        sifnn::cp_async4(w_st + idx, a.w + (ok ? (size_t)(o0 + o) * a.w_so + (size_t)(c0 + ci) * a.w_sk + (a.w_flip ? 8 - t : t) : 0), ok ? 4 : 0);
+    fs.sdst = -1; fs.ssrc = 0; fs.sbytes = 0;
+    const int ps = tid - FS::SOFF;
+    if (ps >= 0 && ps < FS::NS) {
+        const int r = ps >> 1, right = ps & 1;
+        int gy = y0 + r - 1, gx = right ? x0 + TW : x0 - 1;
+        bool ok = true;
+        if (PAD == PAD_REPLICATE) {
+            gy = min(max(gy, 0), H - 1);
+            gx = min(max(gx, 0), W - 1);
+        } else {
+            ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        }
+        fs.sdst = r * IN_STRIDE + (right ? IN_X0 + 1 + TW : IN_X0);
+        fs.ssrc = ok ? gy * W + gx : 0;
+        fs.sbytes = ok ? 4 : 0;
+    }
+}
+
+template <int IN_ROWS>
+__device__ __forceinline__ void conv_fill_vec(float* in_st, const float* src_chunk, size_t plane, int nci, const FillSlots<IN_ROWS>& fs) {
+    constexpr int IN_PLANE = IN_ROWS * IN_STRIDE;
+    using FS = FillSlots<IN_ROWS>;
+#pragma unroll
+    for (int s = 0; s < FS::VSL; ++s) {
+        if (fs.vdst[s] >= 0) {
+            const float* src = src_chunk + fs.vsrc[s];
+            float* dst = in_st + fs.vdst[s];
+            for (int ci = 0; ci < nci; ++ci) {
+                sifnn::cp_async16(dst, src, fs.vbytes[s]);
+                dst += IN_PLANE;
+                src += plane;
+            }
+        }
+    }
+    if (fs.sdst >= 0) {
+        const float* src = src_chunk + fs.ssrc;
+        float* dst = in_st + fs.sdst;
+        for (int ci = 0; ci < nci; ++ci) {
+            sifnn::cp_async4(dst, src, fs.sbytes);
+            dst += IN_PLANE;
+            src += plane;
+        }
     }
 }
 
 // BatchNorm + ReLU of the producing layer applied in place to the elements THIS thread copied
 // (visible to it after cp.async.wait_group, before the CTA barrier).
 template <int IN_ROWS>
-__device__ __forceinline__ void conv_affine_pass(float* in_st, const float* sc_s, const float* sh_s, int c0, int nci, bool vec_ok, int tid) {
+__device__ __forceinline__ void conv_affine_vec(float* in_st, const float* sc, const float* sh, int nci, const FillSlots<IN_ROWS>& fs) {
     constexpr int IN_PLANE = IN_ROWS * IN_STRIDE;
-    if (vec_ok) {
-        for (int idx = tid; idx < nci * IN_ROWS * 10; idx += 256) {
-            const int ci = idx / (IN_ROWS * 10);
-            const int rem = idx - ci * (IN_ROWS * 10);
-            const int r = rem / 10, j = rem - r * 10;
-            const float sc = sc_s[c0 + ci], sh = sh_s[c0 + ci];
-            float* dst = in_st + ci * IN_PLANE + r * IN_STRIDE;
-            if (j < 8) {
-                float4* q = reinterpret_cast<float4*>(dst + IN_X0 + 1 + 4 * j);
-                float4 v = *q;
-                v.x = sifnn::act_affine_relu(v.x, sc, sh); v.y = sifnn::act_affine_relu(v.y, sc, sh);
-                v.z = sifnn::act_affine_relu(v.z, sc, sh); v.w = sifnn::act_affine_relu(v.w, sc, sh);
-                *q = v;
-            } else {
-                float* q = dst + (j == 8 ? IN_X0 : IN_X0 + 1 + TW);
-                *q = sifnn::act_affine_relu(*q, sc, sh);
+    using FS = FillSlots<IN_ROWS>;
+#pragma unroll
+    for (int s = 0; s < FS::VSL; ++s) {
+        if (fs.vdst[s] >= 0) {
+            float* dst = in_st + fs.vdst[s];
+            for (int ci = 0; ci < nci; ++ci) {
+                float4 v = *reinterpret_cast<float4*>(dst);
+                const float c = sc[ci], h = sh[ci];
+                v.x = sifnn::act_affine_relu(v.x, c, h); v.y = sifnn::act_affine_relu(v.y, c, h);
+                v.z = sifnn::act_affine_relu(v.z, c, h); v.w = sifnn::act_affine_relu(v.w, c, h);
+                *reinterpret_cast<float4*>(dst) = v;
+                dst += IN_PLANE;
             }
         }
-    } else {
-        constexpr int IN_COLS = TW + 2;
-        for (int idx = tid; idx < nci * IN_ROWS * IN_COLS; idx += 256) {
-            const int ci = idx / (IN_ROWS * IN_COLS);
-            const int rem = idx - ci * (IN_ROWS * IN_COLS);
-            const int r = rem / IN_COLS, c = rem - r * IN_COLS;
-            float* q = in_st + ci * IN_PLANE + r * IN_STRIDE + IN_X0 + c;
-            *q = sifnn::act_affine_relu(*q, sc_s[c0 + ci], sh_s[c0 + ci]);
+    }
+    if (fs.sdst >= 0) {
+        float* dst = in_st + fs.sdst;
+        for (int ci = 0; ci < nci; ++ci) {
+            *dst = sifnn::act_affine_relu(*dst, sc[ci], sh[ci]);
+            dst += IN_PLANE;
+        }
+    }
+}
+
+// generic (slow) per-element staging: partial tiles in x, W % 4 != 0, unaligned tensors
+template <int IN_ROWS, int PAD>
+__device__ __forceinline__ void conv_fill_generic(float* in_st, const ConvArgs& a, const float* in_b, int c0, int nci, int x0, int y0, int tid) {
+    constexpr int IN_PLANE = IN_ROWS * IN_STRIDE;
+    constexpr int IN_COLS = TW + 2;
+    const int H = a.H, W = a.W;
+    const size_t plane = (size_t)H * W;
+    for (int idx = tid; idx < nci * IN_ROWS * IN_COLS; idx += 256) {
+        const int ci = idx / (IN_ROWS * IN_COLS);
+        const int rem = idx - ci * (IN_ROWS * IN_COLS);
+        const int r = rem / IN_COLS, c = rem - r * IN_COLS;
+        int gy = y0 + r - 1, gx = x0 + c - 1;
+        bool ok = true;
+        if (PAD == PAD_REPLICATE) {
+            gy = min(max(gy, 0), H - 1);
+            gx = min(max(gx, 0), W - 1);
+        } else {
+            ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        }
+        sifnn::cp_async4(in_st + ci * IN_PLANE + r * IN_STRIDE + IN_X0 + c,
+                         in_b + (size_t)(c0 + ci) * plane + (ok ? (size_t)gy * W + gx : 0), ok ? 4 : 0);
+    }
+}
+
+template <int IN_ROWS>
+__device__ __forceinline__ void conv_affine_generic(float* in_st, const float* sc, const float* sh, int nci, int tid) {
+    constexpr int IN_PLANE = IN_ROWS * IN_STRIDE;
+    constexpr int IN_COLS = TW + 2;
+    for (int idx = tid; idx < nci * IN_ROWS * IN_COLS; idx += 256) {
+        const int ci = idx / (IN_ROWS * IN_COLS);
+        const int rem = idx - ci * (IN_ROWS * IN_COLS);
+        const int r = rem / IN_COLS, c = rem - r * IN_COLS;
+        float* q = in_st + ci * IN_PLANE + r * IN_STRIDE + IN_X0 + c;
+        *q = sifnn::act_affine_relu(*q, sc[ci], sh[ci]);
+    }
+}
+
+// weights: w_st[ci][tap][o]; each thread owns fixed (tap, o) slots and walks the chunk's channels
+template <int CO_T>
+struct WSlots {
+    static constexpr int NW = 9 * CO_T;
+    static constexpr int WSL = (NW + 255) / 256;
+    long long src[WSL];  // offset of (o, c = 0, tap) in the weight tensor, or -1 if o >= O (zero-filled)
+};
+
+template <int CO_T>
+__device__ __forceinline__ void conv_make_wslots(WSlots<CO_T>& ws, const ConvArgs& a, int o0, int tid) {
+#pragma unroll
+    for (int s = 0; s < WSlots<CO_T>::WSL; ++s) {
+        const int wi = tid + 256 * s;
+        ws.src[s] = -2;  // unused slot
+        if (wi < WSlots<CO_T>::NW) {
+            const int o = wi % CO_T, t = wi / CO_T;
+            ws.src[s] = (o0 + o < a.O) ? (long long)(o0 + o) * a.w_so + (a.w_flip ? 8 - t : t) : -1;
+        }
+    }
+}
+
+template <int CO_T>
+__device__ __forceinline__ void conv_fill_w(float* w_st, const ConvArgs& a, int c0, int nci, const WSlots<CO_T>& ws, int tid) {
+#pragma unroll
+    for (int s = 0; s < WSlots<CO_T>::WSL; ++s) {
+        if (ws.src[s] != -2) {
+            const bool ok = ws.src[s] >= 0;
+            const float* src = a.w + (ok ? ws.src[s] + (long long)c0 * a.w_sk : 0);
+            float* dst = w_st + tid + 256 * s;
+            for (int ci = 0; ci < nci; ++ci) {
+                sifnn::cp_async4(dst, src, ok ? 4 : 0);
+                dst += 9 * CO_T;
+                if (ok) src += a.w_sk;
+            }
         }
     }
 }
@@ -171,15 +257,32 @@ __global__ void __launch_bounds__(256, 2) conv3x3_kernel(const ConvArgs a) {
         for (int i = tid; i < K; i += 256) { sc_s[i] = __ldg(a.in_scale + i); sh_s[i] = __ldg(a.in_shift + i); }
     }
 
-    float acc[PY][CPT];
+    // accumulators: packed pairs of output channels (FFMA2) when CPT is even, scalars otherwise
+    constexpr bool PACKED = (CPT % 4 == 0);
+    constexpr int NP = PACKED ? CPT / 2 : 1;
+    sifnn::f32x2_t acc2[PY][NP];
+    float acc[PY][PACKED ? 1 : CPT];
 #pragma unroll
-    for (int i = 0; i < PY; ++i)
+    for (int i = 0; i < PY; ++i) {
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < NP; ++j) acc2[i][j] = 0ull;
+#pragma unroll
+        for (int j = 0; j < (PACKED ? 1 : CPT); ++j) acc[i][j] = 0.f;
+    }
+
+    FillSlots<IN_ROWS> fs;
+    WSlots<CO_T> wsl;
+    if (vec_ok) conv_make_slots<IN_ROWS, PAD>(fs, H, W, x0, y0, tid);
+    conv_make_wslots<CO_T>(wsl, a, o0, tid);
+    auto issue_fill = [&](float* in_st, int c0, int nci) {
+        if (vec_ok) conv_fill_vec<IN_ROWS>(in_st, in_b + (size_t)c0 * plane, plane, nci, fs);
+        else conv_fill_generic<IN_ROWS, PAD>(in_st, a, in_b, c0, nci, x0, y0, tid);
+        conv_fill_w<CO_T>(in_st + CI_CHUNK * IN_PLANE, a, c0, nci, wsl, tid);
+        sifnn::cp_async_commit();
+    };
 
     const int nchunks = (K + CI_CHUNK - 1) / CI_CHUNK;
-    conv_issue_fill<IN_ROWS, CO_T, PAD>(smem, smem + CI_CHUNK * IN_PLANE, a, in_b, 0, min(CI_CHUNK, K), x0, y0, o0, vec_ok, tid);
-    sifnn::cp_async_commit();
+    issue_fill(smem, 0, min(CI_CHUNK, K));
 
     for (int ch = 0; ch < nchunks; ++ch) {
         const int c0 = ch * CI_CHUNK;
@@ -187,16 +290,15 @@ __global__ void __launch_bounds__(256, 2) conv3x3_kernel(const ConvArgs a) {
         float* in_s = smem + (ch & 1) * STAGE;
         float* w_s = in_s + CI_CHUNK * IN_PLANE;
         if (ch + 1 < nchunks) {  // prefetch the next chunk into the other stage while this one is consumed
-            float* nin = smem + ((ch + 1) & 1) * STAGE;
-            conv_issue_fill<IN_ROWS, CO_T, PAD>(nin, nin + CI_CHUNK * IN_PLANE, a, in_b, c0 + CI_CHUNK, min(CI_CHUNK, K - c0 - CI_CHUNK), x0, y0, o0, vec_ok, tid);
-            sifnn::cp_async_commit();
+            issue_fill(smem + ((ch + 1) & 1) * STAGE, c0 + CI_CHUNK, min(CI_CHUNK, K - c0 - CI_CHUNK));
             sifnn::cp_async_wait<1>();
         } else {
             sifnn::cp_async_wait<0>();
         }
         if (AFFINE) {
             if (ch == 0) __syncthreads();  // sc_s / sh_s
-            conv_affine_pass<IN_ROWS>(in_s, sc_s, sh_s, c0, nci, vec_ok, tid);
+            if (vec_ok) conv_affine_vec<IN_ROWS>(in_s, sc_s + c0, sh_s + c0, nci, fs);
+            else conv_affine_generic<IN_ROWS>(in_s, sc_s + c0, sh_s + c0, nci, tid);
         }
         __syncthreads();
 
@@ -213,23 +315,31 @@ __global__ void __launch_bounds__(256, 2) conv3x3_kernel(const ConvArgs a) {
             for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    float wv[CPT];
                     const float* wq = wp + (ci * 9 + ky * 3 + kx) * CO_T;
-                    if (CPT % 4 == 0) {
+                    if (PACKED) {
+                        sifnn::f32x2_t w2[NP];
 #pragma unroll
-                        for (int j = 0; j < CPT; j += 4) {
-                            const float4 t4 = *reinterpret_cast<const float4*>(wq + j);
-                            wv[j] = t4.x; wv[j + 1] = t4.y; wv[j + 2] = t4.z; wv[j + 3] = t4.w;
+                        for (int j = 0; j < NP; j += 2) {
+                            const ulonglong2 t2 = *reinterpret_cast<const ulonglong2*>(wq + 2 * j);
+                            w2[j] = t2.x; w2[j + 1] = t2.y;
+                        }
+#pragma unroll
+                        for (int py = 0; py < PY; ++py) {
+                            const float x = v[py + ky][kx];
+                            const sifnn::f32x2_t xx = sifnn::pack2(x, x);
+#pragma unroll
+                            for (int j = 0; j < NP; ++j) acc2[py][j] = sifnn::fma2(xx, w2[j], acc2[py][j]);
                         }
                     } else {
+                        float wv[CPT];
 #pragma unroll
                         for (int j = 0; j < CPT; ++j) wv[j] = wq[j];
-                    }
 #pragma unroll
-                    for (int py = 0; py < PY; ++py) {
-                        const float x = v[py + ky][kx];
+                        for (int py = 0; py < PY; ++py) {
+                            const float x = v[py + ky][kx];
 #pragma unroll
-                        for (int j = 0; j < CPT; ++j) acc[py][j] = fmaf(x, wv[j], acc[py][j]);
+                            for (int j = 0; j < CPT; ++j) acc[py][j] = fmaf(x, wv[j], acc[py][j]);
+                        }
                     }
                 }
             }
@@ -253,7 +363,14 @@ __global__ void __launch_bounds__(256, 2) conv3x3_kernel(const ConvArgs a) {
             for (int py = 0; py < PY; ++py) {
                 const int y = y0 + wr * PY + py;
                 if (xok && y < H) {
-                    float r = acc[py][j] + bv;
+                    float r;
+                    if (PACKED) {
+                        float lo, hi;
+                        sifnn::unpack2(acc2[py][j >> 1], lo, hi);
+                        r = ((j & 1) ? hi : lo) + bv;
+                    } else {
+                        r = acc[py][PACKED ? 0 : j] + bv;
+                    }
                     const size_t off = (size_t)y * W + x;
                     if (a.accumulate) r += op[off];
                     op[off] = r;
@@ -301,13 +418,15 @@ __global__ void __launch_bounds__(256, 2) conv3x3_kernel(const ConvArgs a) {
 // and reused for every k, the weights come from shared memory as broadcast float4.
 // Launched twice (rows, then columns) so the corner pixels are updated without a race.
 constexpr int BORDER_OC = 16;  // output-channel chunk staged in shared memory
+constexpr int BORDER_KC = 32;  // input channels per CTA (4 warps x 8)
 
-__global__ void __launch_bounds__(256) dgrad_border_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+__global__ void __launch_bounds__(128) dgrad_border_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
                                                            int Cin, int Cout, int H, int W, int cols_pass) {
-    extern __shared__ __align__(16) float ws[];  // [BORDER_OC][4 taps (3 main + corner)][Cin_pad]
-    const int Cp = (Cin + 3) & ~3;
+    __shared__ __align__(16) float ws[BORDER_OC * 5 * BORDER_KC];  // [o][slot: 3 main taps + 2 corner taps][k]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
+    const int kc0 = blockIdx.z * BORDER_KC;
+    const int kb = kc0 + warp * 8;
     const int L = cols_pass ? H : W;              // side length
     const int segs = (L + 31) / 32;
     const int side = blockIdx.x / segs;           // 0: top/left, 1: bottom/right
@@ -322,11 +441,11 @@ __global__ void __launch_bounds__(256) dgrad_border_kernel(const float* __restri
         p = i; q = side ? W - 1 : 0;
         t0 = side ? 2 : 0; tstep = 3; r0 = p + 1; dr = -1; c0 = q; dc = 0;
     }
-    // corner cross term (rows pass only): tap (ky_e, kx_e) on dy[r_e][c_e]
-    int tc = -1;
+    // corner cross term (rows pass only): slot 3 = tap (ky_e, 0), slot 4 = tap (ky_e, 2), on dy at the pixel itself
+    int cslot = -1;
     if (!cols_pass && active) {
-        if (q == 0) tc = (side ? 6 : 0);
-        else if (q == W - 1) tc = (side ? 8 : 2);
+        if (q == 0) cslot = 3;
+        else if (q == W - 1) cslot = 4;
     }
     const size_t plane = (size_t)H * W;
     const float* dyb = dy + (size_t)b * Cout * plane;
@@ -338,57 +457,59 @@ __global__ void __launch_bounds__(256) dgrad_border_kernel(const float* __restri
         ok[j] = active && r >= 0 && r < H && c >= 0 && c < W;
         off[j] = ok[j] ? (size_t)r * W + c : 0;
     }
-    const size_t offc = (size_t)p * W + q;  // corner term reads dy at the pixel itself
+    const size_t offc = active ? (size_t)p * W + q : 0;
 
-    for (int kbase = 0; kbase < Cin; kbase += 64) {   // each warp: 8 input channels at a time (loop trip count is CTA-uniform)
-        const int kb = kbase + warp * 8;
-        float acc[8];
+    float acc[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-        for (int ob = 0; ob < Cout; ob += BORDER_OC) {
-            const int no = min(BORDER_OC, Cout - ob);
-            __syncthreads();
-            // stage w[ob..ob+no)[all k][the 3 main taps + both possible corner taps]; layout [o][slot][k]
-            for (int idx = threadIdx.x; idx < no * 5 * Cp; idx += 256) {
-                const int k = idx % Cp;
-                const int slot = (idx / Cp) % 5;
-                const int o = idx / (5 * Cp);
-                int t;
-                if (slot < 3) t = t0 + slot * tstep;
-                else t = (slot == 3) ? (side ? 6 : 0) : (side ? 8 : 2);
-                ws[idx] = (k < Cin) ? __ldg(w + ((size_t)(ob + o) * Cin + k) * 9 + t) : 0.f;
-            }
-            __syncthreads();
-            if (kb < Cin) {
-                for (int o = 0; o < no; ++o) {
-                    const float* dyo = dyb + (size_t)(ob + o) * plane;
-                    float d[4];
+    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+    for (int ob = 0; ob < Cout; ob += BORDER_OC) {
+        const int no = min(BORDER_OC, Cout - ob);
+        // all dy values of this chunk first: BORDER_OC x 4 independent loads in flight while the weights are staged
+        float dv[BORDER_OC][4];
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) d[j] = ok[j] ? __ldg(dyo + off[j]) : 0.f;
-                    d[3] = (tc >= 0) ? __ldg(dyo + offc) : 0.f;
-                    const float* wo = ws + (size_t)o * 5 * Cp + kb;
+        for (int o = 0; o < BORDER_OC; ++o) {
+            const float* dyo = dyb + (size_t)(ob + min(o, no - 1)) * plane;
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const float4 wa = *reinterpret_cast<const float4*>(wo + j * Cp);
-                        const float4 wb = *reinterpret_cast<const float4*>(wo + j * Cp + 4);
-                        acc[0] = fmaf(wa.x, d[j], acc[0]); acc[1] = fmaf(wa.y, d[j], acc[1]);
-                        acc[2] = fmaf(wa.z, d[j], acc[2]); acc[3] = fmaf(wa.w, d[j], acc[3]);
-                        acc[4] = fmaf(wb.x, d[j], acc[4]); acc[5] = fmaf(wb.y, d[j], acc[5]);
-                        acc[6] = fmaf(wb.z, d[j], acc[6]); acc[7] = fmaf(wb.w, d[j], acc[7]);
-                    }
-                    if (tc >= 0) {  // lane-divergent but only the two corner lanes of a rows pass take it
-                        const float* wc = wo + ((tc == 0 || tc == 6) ? 3 : 4) * Cp;
+            for (int j = 0; j < 3; ++j) dv[o][j] = (ok[j] && o < no) ? __ldg(dyo + off[j]) : 0.f;
+            dv[o][3] = (cslot >= 0 && o < no) ? __ldg(dyo + offc) : 0.f;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < no * 5 * BORDER_KC; idx += 128) {
+            const int k = idx % BORDER_KC;
+            const int slot = (idx / BORDER_KC) % 5;
+            const int o = idx / (5 * BORDER_KC);
+            int t;
+            if (slot < 3) t = t0 + slot * tstep;
+            else t = (slot == 3) ? (side ? 6 : 0) : (side ? 8 : 2);
+            ws[idx] = (kc0 + k < Cin) ? __ldg(w + ((size_t)(ob + o) * Cin + kc0 + k) * 9 + t) : 0.f;
+        }
+        __syncthreads();
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) acc[u] = fmaf(wc[u], d[3], acc[u]);
-                    }
+        for (int o = 0; o < BORDER_OC; ++o) {
+            if (o < no) {
+                const float* wo = ws + o * 5 * BORDER_KC + warp * 8;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float4 wa = *reinterpret_cast<const float4*>(wo + j * BORDER_KC);
+                    const float4 wb = *reinterpret_cast<const float4*>(wo + j * BORDER_KC + 4);
+                    const float d = dv[o][j];
+                    acc[0] = fmaf(wa.x, d, acc[0]); acc[1] = fmaf(wa.y, d, acc[1]);
+                    acc[2] = fmaf(wa.z, d, acc[2]); acc[3] = fmaf(wa.w, d, acc[3]);
+                    acc[4] = fmaf(wb.x, d, acc[4]); acc[5] = fmaf(wb.y, d, acc[5]);
+                    acc[6] = fmaf(wb.z, d, acc[6]); acc[7] = fmaf(wb.w, d, acc[7]);
+                }
+                if (cslot >= 0) {  // only the two corner lanes of a rows pass
+                    const float* wc = wo + cslot * BORDER_KC;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[u] = fmaf(wc[u], dv[o][3], acc[u]);
                 }
             }
         }
-        if (active && kb < Cin) {
+    }
+    if (active) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (kb + u < Cin) dx[((size_t)b * Cin + kb + u) * plane + (size_t)p * W + q] += acc[u];
-        }
+        for (int u = 0; u < 8; ++u)
+            if (kb + u < Cin) dx[((size_t)b * Cin + kb + u) * plane + (size_t)p * W + q] += acc[u];
     }
 }
 
@@ -448,12 +569,10 @@ extern "C" int sifnn_conv3x3_dgrad(const float* dy, const float* w, float* dx, i
     a.w_so = 9; a.w_sk = Cin * 9; a.w_flip = 1; a.accumulate = accumulate ? 1 : 0;
     cudaStream_t st = sifnn::as_stream(stream);
     SIFNN_TRY((dispatch_conv<PAD_ZERO, false>(a, st)));
-    const int Cp = (Cin + 3) & ~3;
-    const size_t bsmem = (size_t)BORDER_OC * 5 * (Cp + 8) * sizeof(float);
     for (int cols_pass = 0; cols_pass < 2; ++cols_pass) {
         const int L = cols_pass ? H : W;
-        dim3 grid(2 * ((L + 31) / 32), B);
-        dgrad_border_kernel<<<grid, 256, bsmem, st>>>(dy, w, dx, Cin, Cout, H, W, cols_pass);
+        dim3 grid(2 * ((L + 31) / 32), B, (Cin + BORDER_KC - 1) / BORDER_KC);
+        dgrad_border_kernel<<<grid, 128, 0, st>>>(dy, w, dx, Cin, Cout, H, W, cols_pass);
         if (cols_pass == 0) SIFNN_TRY(sifnn::check_launch("dgrad_border_kernel"));
     }
     return sifnn::check_launch("dgrad_border_kernel");

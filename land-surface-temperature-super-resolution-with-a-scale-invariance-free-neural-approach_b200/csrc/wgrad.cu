@@ -32,6 +32,83 @@ struct WgradArgs {
 
 // cp.async staging of one pixel tile: K_CHUNK input planes with halo (replicate-clamped) and
 // O_CHUNK dy planes (zero-filled outside the image / past the last channel).
+// Fast path: every thread owns at most ONE fixed slot -- a 16 B column group of an input row
+// (threads 0..143), a halo element (160..195) or a 16 B group of a dy row (256..383) -- and
+// walks it over the chunk's channel planes, so the per-tile index arithmetic is a handful of
+// instructions.  The generic per-element path handles tiles that stick out of the image in x.
+__device__ __forceinline__ int wgrad_role(int tid) { return tid < 144 ? 1 : ((tid >= 160 && tid < 196) ? 2 : ((tid >= 256 && tid < 384) ? 3 : 0)); }
+
+template <int O_CHUNK, int K_CHUNK>
+__device__ __forceinline__ void wgrad_fill_vec(float* in_s, float* dy_s, const WgradArgs& a, int b, int x0, int y0, int k0, int o0, int tid) {
+    constexpr int IN_ROWS = WROWS + 2;
+    constexpr int IN_PLANE = IN_ROWS * IN_STRIDE;
+    constexpr int DY_PLANE = WROWS * 32;
+    const int H = a.H, W = a.W, K = a.K, O = a.O;
+    const size_t plane = (size_t)H * W;
+    const int role = wgrad_role(tid);
+    if (role == 1 || role == 2) {
+        int r, dcol, gx;
+        if (role == 1) { r = tid >> 3; const int j = tid & 7; dcol = IN_X0 + 1 + 4 * j; gx = x0 + 4 * j; }
+        else { const int ps = tid - 160; r = ps >> 1; const int right = ps & 1; dcol = right ? IN_X0 + 33 : IN_X0; gx = right ? min(x0 + 32, W - 1) : max(x0 - 1, 0); }
+        const int gy = min(max(y0 + r - 1, 0), H - 1);
+        const int nk = min(K_CHUNK, K - k0);
+        const float* src = a.in + ((size_t)b * K + k0) * plane + (size_t)gy * W + gx;
+        float* dst = in_s + r * IN_STRIDE + dcol;
+#pragma unroll
+        for (int kk = 0; kk < K_CHUNK; ++kk) {
+            const bool ok = kk < nk;
+            if (role == 1) sifnn::cp_async16(dst, ok ? src : a.in, ok ? 16 : 0);
+            else sifnn::cp_async4(dst, ok ? src : a.in, ok ? 4 : 0);
+            dst += IN_PLANE;
+            src += plane;
+        }
+    } else if (role == 3) {
+        const int t = tid - 256;
+        const int r = t >> 3, j = t & 7;
+        const bool rok = y0 + r < H;
+        const int no = min(O_CHUNK, O - o0);
+        const float* src = a.dy + ((size_t)b * O + o0) * plane + (size_t)(rok ? y0 + r : 0) * W + x0 + 4 * j;
+        float* dst = dy_s + r * 32 + 4 * j;
+#pragma unroll
+        for (int oo = 0; oo < O_CHUNK; ++oo) {
+            const bool ok = rok && oo < no;
+            sifnn::cp_async16(dst, ok ? src : a.dy, ok ? 16 : 0);
+            dst += DY_PLANE;
+            src += plane;
+        }
+    }
+}
+
+template <int K_CHUNK>
+__device__ __forceinline__ void wgrad_affine_vec(float* in_s, const float* sc_s, const float* sh_s, int K, int k0, int tid) {
+    constexpr int IN_ROWS = WROWS + 2;
+    constexpr int IN_PLANE = IN_ROWS * IN_STRIDE;
+    const int role = wgrad_role(tid);
+    const int nk = min(K_CHUNK, K - k0);
+    if (role == 1) {
+        float* dst = in_s + (tid >> 3) * IN_STRIDE + IN_X0 + 1 + 4 * (tid & 7);
+#pragma unroll
+        for (int kk = 0; kk < K_CHUNK; ++kk) {
+            if (kk < nk) {
+                float4 v = *reinterpret_cast<float4*>(dst);
+                const float c = sc_s[kk], h = sh_s[kk];
+                v.x = sifnn::act_affine_relu(v.x, c, h); v.y = sifnn::act_affine_relu(v.y, c, h);
+                v.z = sifnn::act_affine_relu(v.z, c, h); v.w = sifnn::act_affine_relu(v.w, c, h);
+                *reinterpret_cast<float4*>(dst) = v;
+            }
+            dst += IN_PLANE;
+        }
+    } else if (role == 2) {
+        const int ps = tid - 160;
+        float* dst = in_s + (ps >> 1) * IN_STRIDE + ((ps & 1) ? IN_X0 + 33 : IN_X0);
+#pragma unroll
+        for (int kk = 0; kk < K_CHUNK; ++kk) {
+            if (kk < nk) *dst = sifnn::act_affine_relu(*dst, sc_s[kk], sh_s[kk]);
+            dst += IN_PLANE;
+        }
+    }
+}
+
 template <int O_CHUNK, int K_CHUNK, int NT>
 __device__ __forceinline__ void wgrad_issue_fill(float* in_s, float* dy_s, const WgradArgs& a, int b, int x0, int y0, int k0, int o0,
                                                  bool vec_ok, int tid) {
@@ -41,26 +118,7 @@ __device__ __forceinline__ void wgrad_issue_fill(float* in_s, float* dy_s, const
     const int H = a.H, W = a.W, K = a.K, O = a.O;
     const size_t plane = (size_t)H * W;
     if (vec_ok) {
-        for (int idx = tid; idx < K_CHUNK * IN_ROWS * 10; idx += NT) {
-            const int kk = idx / (IN_ROWS * 10);
-            const int rem = idx - kk * (IN_ROWS * 10);
-            const int r = rem / 10, j = rem - r * 10;
-            const bool ok = k0 + kk < K;
-            const int gy = min(max(y0 + r - 1, 0), H - 1);
-            const float* src = a.in + ((size_t)b * K + (ok ? k0 + kk : 0)) * plane + (size_t)gy * W;
-            float* dst = in_s + kk * IN_PLANE + r * IN_STRIDE;
-            if (j < 8) sifnn::cp_async16(dst + IN_X0 + 1 + 4 * j, src + x0 + 4 * j, ok ? 16 : 0);
-            else if (j == 8) sifnn::cp_async4(dst + IN_X0, src + max(x0 - 1, 0), ok ? 4 : 0);
-            else sifnn::cp_async4(dst + IN_X0 + 33, src + min(x0 + 32, W - 1), ok ? 4 : 0);
-        }
-        for (int idx = tid; idx < O_CHUNK * WROWS * 8; idx += NT) {
-            const int oo = idx / (WROWS * 8);
-            const int rem = idx - oo * (WROWS * 8);
-            const int r = rem >> 3, j = rem & 7;
-            const bool ok = (o0 + oo < O) && (y0 + r < H);
-            const float* src = a.dy + ((size_t)b * O + (ok ? o0 + oo : 0)) * plane + (size_t)(ok ? y0 + r : 0) * W + x0 + 4 * j;
-            sifnn::cp_async16(dy_s + oo * DY_PLANE + r * 32 + 4 * j, src, ok ? 16 : 0);
-        }
+        wgrad_fill_vec<O_CHUNK, K_CHUNK>(in_s, dy_s, a, b, x0, y0, k0, o0, tid);
     } else {
         for (int idx = tid; idx < K_CHUNK * IN_ROWS * IN_COLS; idx += NT) {
             const int kk = idx / (IN_ROWS * IN_COLS);
@@ -87,24 +145,7 @@ __device__ __forceinline__ void wgrad_affine_pass(float* in_s, const float* sc_s
     constexpr int IN_ROWS = WROWS + 2;
     constexpr int IN_PLANE = IN_ROWS * IN_STRIDE;
     if (vec_ok) {
-        for (int idx = tid; idx < K_CHUNK * IN_ROWS * 10; idx += NT) {
-            const int kk = idx / (IN_ROWS * 10);
-            const int rem = idx - kk * (IN_ROWS * 10);
-            const int r = rem / 10, j = rem - r * 10;
-            if (k0 + kk >= K) continue;  // zero-filled planes stay zero (they meet zero... any dy, result unused)
-            const float sc = sc_s[kk], sh = sh_s[kk];
-            float* dst = in_s + kk * IN_PLANE + r * IN_STRIDE;
-            if (j < 8) {
-                float4* q = reinterpret_cast<float4*>(dst + IN_X0 + 1 + 4 * j);
-                float4 v = *q;
-                v.x = sifnn::act_affine_relu(v.x, sc, sh); v.y = sifnn::act_affine_relu(v.y, sc, sh);
-                v.z = sifnn::act_affine_relu(v.z, sc, sh); v.w = sifnn::act_affine_relu(v.w, sc, sh);
-                *q = v;
-            } else {
-                float* q = dst + (j == 8 ? IN_X0 : IN_X0 + 33);
-                *q = sifnn::act_affine_relu(*q, sc, sh);
-            }
-        }
+        wgrad_affine_vec<K_CHUNK>(in_s, sc_s, sh_s, K, k0, tid);
     } else {
         for (int idx = tid; idx < K_CHUNK * IN_ROWS * IN_COLS; idx += NT) {
             const int kk = idx / (IN_ROWS * IN_COLS);
@@ -142,10 +183,13 @@ __global__ void __launch_bounds__((O_CHUNK / OT) * (K_CHUNK / KT) * 32, 1) wgrad
     }
 
     float acc[OT][KT][9];
+    sifnn::f32x2_t acc2[OT][9];  // KT == 2: (k0, k1) pairs, used instead of acc
     float bsum[OT];
 #pragma unroll
     for (int j = 0; j < OT; ++j) {
         bsum[j] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc2[j][t] = 0ull;
 #pragma unroll
         for (int k = 0; k < KT; ++k)
 #pragma unroll
@@ -191,40 +235,73 @@ __global__ void __launch_bounds__((O_CHUNK / OT) * (K_CHUNK / KT) * 32, 1) wgrad
 
         const float* ip = in_s + (kt * KT) * IN_PLANE + IN_X0 + lane;
         const float* dp = dy_s + (ot * OT) * DY_PLANE + lane;
-        float win[KT][3][3];
-#pragma unroll
-        for (int k = 0; k < KT; ++k)
+        if (KT == 2) {
+            // packed path (FFMA2): each accumulator pair holds the two input channels of this warp's k-tile;
+            // dy is the scalar-broadcast operand.
+            sifnn::f32x2_t win2[3][3];
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                win[k][0][kx] = ip[k * IN_PLANE + 0 * IN_STRIDE + kx];
-                win[k][1][kx] = ip[k * IN_PLANE + 1 * IN_STRIDE + kx];
+                win2[0][kx] = sifnn::pack2(ip[0 * IN_STRIDE + kx], ip[IN_PLANE + 0 * IN_STRIDE + kx]);
+                win2[1][kx] = sifnn::pack2(ip[1 * IN_STRIDE + kx], ip[IN_PLANE + 1 * IN_STRIDE + kx]);
             }
 #pragma unroll
-        for (int r = 0; r < WROWS; ++r) {
+            for (int r = 0; r < WROWS; ++r) {
 #pragma unroll
-            for (int k = 0; k < KT; ++k)
+                for (int kx = 0; kx < 3; ++kx) win2[2][kx] = sifnn::pack2(ip[(r + 2) * IN_STRIDE + kx], ip[IN_PLANE + (r + 2) * IN_STRIDE + kx]);
+                float d[OT];
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) win[k][2][kx] = ip[k * IN_PLANE + (r + 2) * IN_STRIDE + kx];
-            float d[OT];
+                for (int j = 0; j < OT; ++j) d[j] = dp[j * DY_PLANE + r * 32];
 #pragma unroll
-            for (int j = 0; j < OT; ++j) d[j] = dp[j * DY_PLANE + r * 32];
-#pragma unroll
-            for (int j = 0; j < OT; ++j) {
-                if (BIAS) bsum[j] += d[j];
-#pragma unroll
-                for (int k = 0; k < KT; ++k)
+                for (int j = 0; j < OT; ++j) {
+                    if (BIAS) bsum[j] += d[j];
+                    const sifnn::f32x2_t dd = sifnn::pack2(d[j], d[j]);
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) acc[j][k][ky * 3 + kx] = fmaf(d[j], win[k][ky][kx], acc[j][k][ky * 3 + kx]);
+                        for (int kx = 0; kx < 3; ++kx) acc2[j][ky * 3 + kx] = sifnn::fma2(dd, win2[ky][kx], acc2[j][ky * 3 + kx]);
+                }
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    win2[0][kx] = win2[1][kx];
+                    win2[1][kx] = win2[2][kx];
+                }
             }
+        } else {
+            float win[KT][3][3];
 #pragma unroll
             for (int k = 0; k < KT; ++k)
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    win[k][0][kx] = win[k][1][kx];
-                    win[k][1][kx] = win[k][2][kx];
+                    win[k][0][kx] = ip[k * IN_PLANE + 0 * IN_STRIDE + kx];
+                    win[k][1][kx] = ip[k * IN_PLANE + 1 * IN_STRIDE + kx];
                 }
+#pragma unroll
+            for (int r = 0; r < WROWS; ++r) {
+#pragma unroll
+                for (int k = 0; k < KT; ++k)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) win[k][2][kx] = ip[k * IN_PLANE + (r + 2) * IN_STRIDE + kx];
+                float d[OT];
+#pragma unroll
+                for (int j = 0; j < OT; ++j) d[j] = dp[j * DY_PLANE + r * 32];
+#pragma unroll
+                for (int j = 0; j < OT; ++j) {
+                    if (BIAS) bsum[j] += d[j];
+#pragma unroll
+                    for (int k = 0; k < KT; ++k)
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) acc[j][k][ky * 3 + kx] = fmaf(d[j], win[k][ky][kx], acc[j][k][ky * 3 + kx]);
+                }
+#pragma unroll
+                for (int k = 0; k < KT; ++k)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        win[k][0][kx] = win[k][1][kx];
+                        win[k][1][kx] = win[k][2][kx];
+                    }
+            }
         }
         __syncthreads();  // stage may be refilled by the prefetch of the iteration after next
     }
@@ -237,7 +314,13 @@ __global__ void __launch_bounds__((O_CHUNK / OT) * (K_CHUNK / KT) * 32, 1) wgrad
             const int kk = k0 + kt * KT + k;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-                const float v = sifnn::warp_sum(acc[j][k][t]);
+                float av = acc[j][k][t];
+                if (KT == 2) {
+                    float lo, hi;
+                    sifnn::unpack2(acc2[j][t], lo, hi);
+                    av = k ? hi : lo;
+                }
+                const float v = sifnn::warp_sum(av);
                 if (lane == 0 && o < O && kk < K) a.partial[(((size_t)s * O + o) * K + kk) * 9 + t] = v;
             }
         }
