@@ -54,6 +54,14 @@ __device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
     return d;
 }
 
+// same, but `volatile`: ptxas keeps the program order of these among themselves, which is how the kernels pin the
+// operand-reuse-friendly (weight-stationary) issue order
+__device__ __forceinline__ f32x2_t fma2_ordered(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t d;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 __device__ __forceinline__ float act_affine_relu(float x, float sc, float sh) { return fmaxf(fmaf(x, sc, sh), 0.0f); }
 
 }  // namespace sifnn

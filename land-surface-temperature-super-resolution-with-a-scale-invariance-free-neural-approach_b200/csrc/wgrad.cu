@@ -251,15 +251,19 @@ __global__ void __launch_bounds__((O_CHUNK / OT) * (K_CHUNK / KT) * 32, 1) wgrad
                 float d[OT];
 #pragma unroll
                 for (int j = 0; j < OT; ++j) d[j] = dp[j * DY_PLANE + r * 32];
+                if (BIAS) {
 #pragma unroll
-                for (int j = 0; j < OT; ++j) {
-                    if (BIAS) bsum[j] += d[j];
-                    const sifnn::f32x2_t dd = sifnn::pack2(d[j], d[j]);
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) acc2[j][ky * 3 + kx] = sifnn::fma2(dd, win2[ky][kx], acc2[j][ky * 3 + kx]);
+                    for (int j = 0; j < OT; ++j) bsum[j] += d[j];
                 }
+                // window-stationary order: the 64-bit window pair stays in the operand-reuse cache across the OT
+                // dy scalars (see tools/ffma2_probe2.cu)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int j = 0; j < OT; ++j)
+                            acc2[j][ky * 3 + kx] = sifnn::fma2(sifnn::pack2(d[j], d[j]), win2[ky][kx], acc2[j][ky * 3 + kx]);
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     win2[0][kx] = win2[1][kx];
