@@ -13,5 +13,6 @@ from .model import (ModelB_2, DoubleConvolution, UpBlock, ResidualConnection, Do
                     ResBridgeBlock, Serf, activation_functions, bicubic4_cat)
 from .losses import sr_losses, sr1_losses, sr2_losses, loss_fwd_bwd  # noqa: F401
 from .trainer import Trainer  # noqa: F401
+from .parallel import block_partition, shard_batch, BucketedAllReduce  # noqa: F401
 
 __version__ = "0.1.0"

@@ -22,6 +22,7 @@ from . import _lib
 from ._lib import SifnnError
 from .losses import loss_fwd_bwd
 from .model import ModelB_2, bicubic4_cat, _stream
+from .parallel import BucketedAllReduce
 
 
 class Trainer:
@@ -63,12 +64,12 @@ class Trainer:
         st, opt = self._opt_state(x.device)
         fgrad, dec = st["fgrad"], st["dec_off"]
         if self.world > 1 and self.overlap:
+            ar = BucketedAllReduce(fgrad, dec)
             m._run_backward(x, dsr, ws, phase=1)
-            w1 = dist.all_reduce(fgrad[dec:], async_op=True)      # decoder bucket, overlaps the encoder backward
+            ar.start(0)                                            # decoder bucket, overlaps the encoder backward
             m._run_backward(x, dsr, ws, phase=2)
-            w2 = dist.all_reduce(fgrad[:dec], async_op=True)
-            w1.wait()
-            w2.wait()
+            ar.start(1)
+            ar.finish()
         else:
             m._run_backward(x, dsr, ws, phase=0)
             if self.world > 1:
