@@ -55,6 +55,25 @@ int sifnn_conv3x3_fwd(const float* in, const float* in_scale, const float* in_sh
 int sifnn_conv3x3_dgrad(const float* dy, const float* w, float* dx, int accumulate,
                         int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
 
+/* Tensor-core variants (tcgen05 / TMEM implicit GEMM, 3-term TF32 split: fp32-accurate).  Same semantics as
+ * sifnn_conv3x3_fwd / the zero-padded main part of sifnn_conv3x3_dgrad, for shapes where
+ * sifnn_conv3x3_tc_supported() != 0 (W % 128 == 0, Cin % 8 == 0, Cout in {16,32,64}).  wprep: caller-owned
+ * scratch of sifnn_conv3x3_tc_wprep_bytes() bytes that receives the hi/lo-split weights of the call.
+ * sifnn_conv3x3_dgrad_tc_main does NOT add the replicate-padding border terms; sifnn_conv3x3_dgrad_tc does
+ * (same kernel + the border pass of the SIMT path). */
+int sifnn_conv3x3_tc_supported(int Cin, int Cout, int H, int W);
+size_t sifnn_conv3x3_tc_wprep_bytes(int Cin, int Cout);
+int sifnn_conv3x3_fwd_tc(const float* in, const float* in_scale, const float* in_shift,
+                         const float* w, const float* bias, float* out, double* stats, void* wprep,
+                         int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+int sifnn_conv3x3_dgrad_tc_main(const float* dy, const float* w, float* dx, int accumulate, void* wprep,
+                                int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+int sifnn_conv3x3_dgrad_tc(const float* dy, const float* w, float* dx, int accumulate, void* wprep,
+                           int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+/* The border pass alone: dx += adjoint-of-replicate-padding terms (used after a *_main call). */
+int sifnn_conv3x3_dgrad_border(const float* dy, const float* w, float* dx,
+                               int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+
 /* Weight gradient.  `in`/in_scale/in_shift as in sifnn_conv3x3_fwd.  dw (Cout,Cin,3,3)
  * is overwritten; dbias (Cout) or NULL.  workspace: sifnn_conv3x3_wgrad_workspace()
  * bytes of scratch (per-CTA partial sums, reduced in a fixed order -> deterministic). */

@@ -573,6 +573,13 @@ extern "C" int sifnn_conv3x3_dgrad(const float* dy, const float* w, float* dx, i
     a.w_so = 9; a.w_sk = Cin * 9; a.w_flip = 1; a.accumulate = accumulate ? 1 : 0;
     cudaStream_t st = sifnn::as_stream(stream);
     SIFNN_TRY((dispatch_conv<PAD_ZERO, false>(a, st)));
+    return sifnn_conv3x3_dgrad_border(dy, w, dx, B, Cin, Cout, H, W, stream);
+}
+
+extern "C" int sifnn_conv3x3_dgrad_border(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H, int W,
+                                          sifnn_stream_t stream) {
+    SIFNN_REQUIRE(dy && w && dx && B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && H >= 2 && W >= 2, "conv3x3_dgrad_border: bad arguments");
+    cudaStream_t st = sifnn::as_stream(stream);
     for (int cols_pass = 0; cols_pass < 2; ++cols_pass) {
         const int L = cols_pass ? H : W;
         dim3 grid(2 * ((L + 31) / 32), B, (Cin + BORDER_KC - 1) / BORDER_KC);
@@ -580,4 +587,10 @@ extern "C" int sifnn_conv3x3_dgrad(const float* dy, const float* w, float* dx, i
         if (cols_pass == 0) SIFNN_TRY(sifnn::check_launch("dgrad_border_kernel"));
     }
     return sifnn::check_launch("dgrad_border_kernel");
+}
+
+extern "C" int sifnn_conv3x3_dgrad_tc(const float* dy, const float* w, float* dx, int accumulate, void* wprep, int B, int Cin, int Cout,
+                                      int H, int W, sifnn_stream_t stream) {
+    SIFNN_TRY(sifnn_conv3x3_dgrad_tc_main(dy, w, dx, accumulate, wprep, B, Cin, Cout, H, W, stream));
+    return sifnn_conv3x3_dgrad_border(dy, w, dx, B, Cin, Cout, H, W, stream);
 }

@@ -1,0 +1,65 @@
+"""tcgen05 / TMEM implicit-GEMM convolution (3-term TF32 split) against torch fp64 (-m gpu)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import sifnn_b200
+from sifnn_b200 import ops
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def ref_conv(x, w, b=None):
+    return F.conv2d(F.pad(x.double(), (1, 1, 1, 1), mode="replicate"), w.double(), None if b is None else b.double())
+
+
+SHAPES = [(2, 16, 16, 8, 128), (1, 32, 16, 6, 256), (2, 64, 32, 5, 128), (1, 8, 64, 4, 128), (3, 16, 32, 16, 128), (1, 128, 64, 3, 128)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_tc_fwd_plain(shape):
+    B, Cin, Cout, H, W = shape
+    x, w = rnd(B, Cin, H, W, seed=1), rnd(Cout, Cin, 3, 3, seed=2, scale=0.2)
+    y = ops.conv3x3_fwd_tc(x.cuda(), w.cuda())
+    assert rel_err(y, ref_conv(x, w)) < TOL
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 8, 128), (1, 32, 64, 6, 256)])
+def test_tc_fwd_affine_stats_bias(shape):
+    B, Cin, Cout, H, W = shape
+    x, w = rnd(B, Cin, H, W, seed=4), rnd(Cout, Cin, 3, 3, seed=5, scale=0.2)
+    sc, sh, bias = 1 + 0.3 * rnd(Cin, seed=6), 0.2 * rnd(Cin, seed=7), rnd(Cout, seed=8)
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    y = ops.conv3x3_fwd_tc(x.cuda(), w.cuda(), bias.cuda(), sc.cuda(), sh.cuda(), stats)
+    a = F.relu(x.double() * sc.double()[None, :, None, None] + sh.double()[None, :, None, None])
+    ref = ref_conv(a, w, bias)
+    assert rel_err(y, ref) < TOL
+    assert rel_err(stats[:Cout], ref.sum((0, 2, 3))) < 1e-4
+    assert rel_err(stats[Cout:], (ref * ref).sum((0, 2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 8, 128), (1, 16, 32, 6, 256), (2, 64, 32, 5, 128), (1, 32, 64, 4, 128)])
+def test_tc_dgrad(shape):
+    B, Cin, Cout, H, W = shape
+    w, dy = rnd(Cout, Cin, 3, 3, seed=8, scale=0.2), rnd(B, Cout, H, W, seed=9)
+    x = torch.zeros(B, Cin, H, W, dtype=torch.float64, requires_grad=True)
+    (ref_conv(x, w) * dy.double()).sum().backward()
+    dx = ops.conv3x3_dgrad_tc(dy.cuda(), w.cuda())
+    assert rel_err(dx, x.grad) < TOL
+    base = rnd(B, Cin, H, W, seed=10)
+    acc = ops.conv3x3_dgrad_tc(dy.cuda(), w.cuda(), base.cuda().clone(), accumulate=True)
+    assert rel_err(acc, x.grad + base.double()) < TOL
+
+
+def test_tc_matches_simt_closely():
+    """Same inputs through the SIMT fp32 kernel and the 3xTF32 tensor-core kernel."""
+    x, w = rnd(2, 32, 32, 256, seed=11).cuda(), rnd(16, 32, 3, 3, seed=12, scale=0.2).cuda()
+    a, b = ops.conv3x3_fwd(x, w), ops.conv3x3_fwd_tc(x, w)
+    assert rel_err(b, a) < 5e-6
