@@ -119,6 +119,7 @@ struct TcArgs {
     double* stats;
     int B, K, O, H, W;
     int accumulate;
+    int dbg;  // timing experiments only: 1 = skip the MMAs, 2 = issue every MMA twice
 };
 
 template <int N, int R>
@@ -128,14 +129,14 @@ struct TcSmem {
     static constexpr int B_TILE = 9 * 2 * 2 * N * 4;          // floats: [9 taps][2 q][2N rows][4]
     static constexpr int STAGE = 2 * A_TILE + B_TILE;
     static constexpr int CTRL_FLOATS = 512;  // barriers, TMEM slot, BatchNorm scale/shift (2 KB)
-    static constexpr int BUDGET = 200 * 1024;
+    static constexpr int BUDGET = (N <= 32) ? 112 * 1024 : 200 * 1024;  // N <= 32: two CTAs per SM
     static constexpr int STAGES = (STAGE * 4 * 4 + 2048 <= BUDGET) ? 4 : ((STAGE * 4 * 3 + 2048 <= BUDGET) ? 3 : 2);
     static constexpr size_t BYTES = (size_t)STAGES * STAGE * 4 + CTRL_FLOATS * 4;
     static constexpr int TMEM_COLS = (R * 2 * N <= 32) ? 32 : (R * 2 * N <= 64) ? 64 : (R * 2 * N <= 128) ? 128 : (R * 2 * N <= 256) ? 256 : 512;
 };
 
 template <int N, int R, int PAD, bool AFFINE>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, (N <= 32) ? 2 : 1) conv3x3_tc_kernel(const TcArgs a) {
     using SM = TcSmem<N, R>;
     constexpr int TROWS = SM::TROWS;
     constexpr int S = SM::STAGES;
@@ -178,18 +179,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcArgs 
 
     if (warp < 8) {
         // =============================== producers: stage A (and kick the weight bulk copy) ===============================
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int s = ch % S;
-            float* a_hi = stage0 + (size_t)s * SM::STAGE;
-            float* a_lo = a_hi + SM::A_TILE;
-            float* b_st = a_lo + SM::A_TILE;
-            if (ch >= S) mbar_wait(empty_bar + s, ((ch / S) - 1) & 1);
-            if (tid == 0) {
-                mbar_arrive_expect_tx(full_bar + s, SM::B_TILE * 4);
-                bulk_g2s(b_st, a.wprep + (size_t)ch * SM::B_TILE, SM::B_TILE * 4, full_bar + s);
-            }
-            const int c0 = ch * TC_KC;
-            for (int it = tid; it < 2 * TROWS * TC_PITCH; it += TC_PRODUCERS) {
+        // Each thread owns NIT fixed (channel quad, tile row, pixel) items.  All 4*NIT global loads of a chunk are issued
+        // before anything is consumed, and the loads of chunk ch+1 are in flight while chunk ch is split and stored.
+        constexpr int ITEMS = 2 * TROWS * TC_PITCH;
+        constexpr int NIT = (ITEMS + TC_PRODUCERS - 1) / TC_PRODUCERS;
+        int goff[NIT];   // pixel offset inside a channel plane, -1: zero-filled / unused item
+        int cq[NIT];     // channel quad (0/1) of the item
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            const int it = tid + i * TC_PRODUCERS;
+            goff[i] = -1; cq[i] = 0;
+            if (it < ITEMS) {
                 const int q = it / (TROWS * TC_PITCH);
                 const int rem = it - q * (TROWS * TC_PITCH);
                 const int rr = rem / TC_PITCH, px = rem - rr * TC_PITCH;
@@ -201,22 +201,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcArgs 
                 } else {
                     ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
                 }
-                float v[4], hi[4], lo[4];
-                const float* src = in_b + (size_t)(c0 + 4 * q) * plane + (ok ? (size_t)gy * W + gx : 0);
+                cq[i] = q;
+                goff[i] = ok ? gy * W + gx : -1;
+            }
+        }
+        float v[NIT][4], vn[NIT][4];
+        auto load_chunk = [&](int ch, float (&dst)[NIT][4]) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = ok ? __ldg(src + (size_t)e * plane) : 0.f;
+            for (int i = 0; i < NIT; ++i) {
+                const float* src = in_b + (size_t)(ch * TC_KC + 4 * cq[i]) * plane + (goff[i] >= 0 ? goff[i] : 0);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float t = v[e];
-                    if (AFFINE) t = sifnn::act_affine_relu(t, sc_s[c0 + 4 * q + e], sh_s[c0 + 4 * q + e]);
-                    hi[e] = tf32_hi(t);
-                    lo[e] = t - hi[e];
+                for (int e = 0; e < 4; ++e) dst[i][e] = goff[i] >= 0 ? __ldg(src + (size_t)e * plane) : 0.f;
+            }
+        };
+        load_chunk(0, v);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int s = ch % S;
+            float* a_hi = stage0 + (size_t)s * SM::STAGE;
+            float* a_lo = a_hi + SM::A_TILE;
+            float* b_st = a_lo + SM::A_TILE;
+            if (ch + 1 < nchunks) load_chunk(ch + 1, vn);
+            if (ch >= S) mbar_wait(empty_bar + s, ((ch / S) - 1) & 1);
+            if (tid == 0) {
+                mbar_arrive_expect_tx(full_bar + s, SM::B_TILE * 4);
+                bulk_g2s(b_st, a.wprep + (size_t)ch * SM::B_TILE, SM::B_TILE * 4, full_bar + s);
+            }
+            const int c0 = ch * TC_KC;
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) {
+                const int it = tid + i * TC_PRODUCERS;
+                if (it < ITEMS) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float t = v[i][e];
+                        if (AFFINE && goff[i] >= 0) t = sifnn::act_affine_relu(t, sc_s[c0 + 4 * cq[i] + e], sh_s[c0 + 4 * cq[i] + e]);
+                        hi[e] = tf32_hi(t);
+                        lo[e] = t - hi[e];
+                    }
+                    *reinterpret_cast<float4*>(a_hi + (size_t)it * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(a_lo + (size_t)it * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
-                *reinterpret_cast<float4*>(a_hi + (size_t)it * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(a_lo + (size_t)it * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
             fence_proxy_async();  // generic-proxy st.shared -> visible to the tensor core (async proxy)
             mbar_arrive(full_bar + s);
+#pragma unroll
+            for (int i = 0; i < NIT; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[i][e] = vn[i][e];
         }
     } else {
         // =============================== MMA issuer (one thread) ===============================
@@ -239,8 +271,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcArgs 
                         const uint32_t aoff = ((r + ky) * TC_PITCH + kx) * 16;
                         const uint64_t db = make_desc(b_st + t * (2 * 2 * N * 16), LBO_B, SBO);
                         const uint32_t d = tmem_base + r * 2 * N;
+                        if (a.dbg == 1) continue;
                         umma_tf32(d, make_desc(a_hi + aoff, LBO_A, SBO), db, idesc1, (ch | t) != 0);
                         umma_tf32(d, make_desc(a_lo + aoff, LBO_A, SBO), db, idesc2, 1);
+                        if (a.dbg == 2) {
+                            umma_tf32(d, make_desc(a_hi + aoff, LBO_A, SBO), db, idesc1, 1);
+                            umma_tf32(d, make_desc(a_lo + aoff, LBO_A, SBO), db, idesc2, 1);
+                        }
                     }
                 }
                 umma_commit(empty_bar + s);                       // stage free once these MMAs have read it
@@ -360,6 +397,9 @@ int dispatch_tc(const TcArgs& a, cudaStream_t st) {
 
 }  // namespace
 
+static int g_tc_dbg = 0;
+extern "C" void sifnn_tc_debug(int mode) { g_tc_dbg = mode; }
+
 extern "C" int sifnn_conv3x3_tc_supported(int Cin, int Cout, int H, int W) {
     return (W % 128 == 0) && (Cin % 8 == 0) && Cin <= 128 && (Cout == 16 || Cout == 32 || Cout == 64) && H >= 1;
 }
@@ -377,7 +417,7 @@ extern "C" int sifnn_conv3x3_fwd_tc(const float* in, const float* in_scale, cons
     SIFNN_TRY(sifnn::check_launch("tc_prep_weights_kernel"));
     TcArgs a{};
     a.in = in; a.in_scale = in_scale; a.in_shift = in_shift; a.wprep = static_cast<const float*>(wprep); a.bias = bias; a.out = out; a.stats = stats;
-    a.B = B; a.K = Cin; a.O = Cout; a.H = H; a.W = W; a.accumulate = 0;
+    a.B = B; a.K = Cin; a.O = Cout; a.H = H; a.W = W; a.accumulate = 0; a.dbg = g_tc_dbg;
     return in_scale ? dispatch_tc<0, true>(a, st) : dispatch_tc<0, false>(a, st);
 }
 
@@ -392,6 +432,6 @@ extern "C" int sifnn_conv3x3_dgrad_tc_main(const float* dy, const float* w, floa
     SIFNN_TRY(sifnn::check_launch("tc_prep_weights_kernel"));
     TcArgs a{};
     a.in = dy; a.wprep = static_cast<const float*>(wprep); a.out = dx;
-    a.B = B; a.K = Cout; a.O = Cin; a.H = H; a.W = W; a.accumulate = accumulate ? 1 : 0;
+    a.B = B; a.K = Cout; a.O = Cin; a.H = H; a.W = W; a.accumulate = accumulate ? 1 : 0; a.dbg = g_tc_dbg;
     return dispatch_tc<1, false>(a, st);
 }

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--tc", action="store_true", help="compare the tcgen05 kernels with the SIMT ones on the eligible layers")
     a = ap.parse_args()
     B = a.batch
     peak = ops.fp32_peak_tflops() if a.time else 0.0
@@ -39,6 +40,18 @@ def main():
         fns = {"fwd": lambda: ops.conv3x3_fwd(x, w), "fwd_aff": lambda: ops.conv3x3_fwd(x, w, None, sc, sh),
                "dgrad": lambda: ops.conv3x3_dgrad(dy, w), "wgrad": lambda: ops.conv3x3_wgrad(x, dy, want_bias=(co == 1)),
                "wgrad_aff": lambda: ops.conv3x3_wgrad(x, dy, sc, sh, want_bias=(co == 1))}
+        lib = sifnn_b200.load()
+        if a.tc:
+            fns = {}
+            if lib.sifnn_conv3x3_tc_supported(ci, co, hw, hw):
+                fns["fwd"] = lambda: ops.conv3x3_fwd(x, w)
+                fns["fwd_tc"] = lambda: ops.conv3x3_fwd_tc(x, w)
+                fns["fwd_aff_tc"] = lambda: ops.conv3x3_fwd_tc(x, w, None, sc, sh)
+            if lib.sifnn_conv3x3_tc_supported(co, ci, hw, hw):
+                fns["dgrad"] = lambda: ops.conv3x3_dgrad(dy, w)
+                fns["dgrad_tc"] = lambda: ops.conv3x3_dgrad_tc(dy, w)
+            if not fns:
+                continue
         row = []
         for name, fn in fns.items():
             fn()
