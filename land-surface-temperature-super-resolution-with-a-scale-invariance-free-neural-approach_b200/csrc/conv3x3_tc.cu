@@ -20,12 +20,12 @@
 //   tcgen05.commit; warps 0..7 then read the accumulators back (tcgen05.ld) for the epilogue.
 #include "common.cuh"
 
+#include <cuda.h>  // CUtensorMap types only; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint (no libcuda link)
+
 namespace {
 
 constexpr int TC_PITCH = 130;      // 128 pixels + 2 halo columns
 constexpr int TC_KC = 8;           // channels per pipeline stage = one MMA K step (TF32: 32 bytes)
-constexpr int TC_PRODUCERS = 256;  // threads staging A
-constexpr int TC_THREADS = TC_PRODUCERS + 32;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -55,6 +55,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// one TMA box load: 3-D tile {x, y, plane} of the activation tensor -> shared memory, out-of-bounds elements zero-filled
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int x, int y, int z, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -119,8 +126,17 @@ struct TcArgs {
     double* stats;
     int B, K, O, H, W;
     int accumulate;
-    int dbg;  // timing experiments only: 1 = skip the MMAs, 2 = issue every MMA twice
+    int tiles_x, tiles_y, num_tiles;
 };
+
+// Warp roles of the persistent kernel (18 warps)
+constexpr int TC_EPI_WARPS = 8;     // warps 0..7 : epilogue (TMEM lane quadrant = warp % 4, channel half = warp / 4)
+constexpr int TC_LOAD_WARP = 8;     // warp 8     : bulk-copies raw activation rows (global -> shared, TMA unit)
+constexpr int TC_MMA_WARP = 9;      // warp 9     : issues tcgen05.mma / tcgen05.commit from one thread
+constexpr int TC_XF_WARP0 = 10;     // warps 10..17: transform raw rows -> (BatchNorm, ReLU) -> TF32 hi/lo pixel-major tiles
+constexpr int TC_XF_THREADS = 256;
+constexpr int TC_THREADS2 = (TC_XF_WARP0 + 8) * 32;
+constexpr int TC_RAW_ROW = 136;     // floats per staged raw row: gx = x0-4 .. x0+131 (16-byte aligned both ends)
 
 template <int N, int R>
 struct TcSmem {
@@ -128,226 +144,239 @@ struct TcSmem {
     static constexpr int A_TILE = 2 * TROWS * TC_PITCH * 4;  // floats per (hi or lo) tile: [2 q][TROWS*PITCH px][4]
     static constexpr int B_TILE = 9 * 2 * 2 * N * 4;          // floats: [9 taps][2 q][2N rows][4]
     static constexpr int STAGE = 2 * A_TILE + B_TILE;
+    static constexpr int RAW_STAGE = TC_KC * TROWS * TC_RAW_ROW;  // floats
+    static constexpr int RAW_STAGES = 3;
     static constexpr int CTRL_FLOATS = 512;  // barriers, TMEM slot, BatchNorm scale/shift (2 KB)
-    static constexpr int BUDGET = (N <= 32) ? 112 * 1024 : 200 * 1024;  // N <= 32: two CTAs per SM
-    static constexpr int STAGES = (STAGE * 4 * 4 + 2048 <= BUDGET) ? 4 : ((STAGE * 4 * 3 + 2048 <= BUDGET) ? 3 : 2);
-    static constexpr size_t BYTES = (size_t)STAGES * STAGE * 4 + CTRL_FLOATS * 4;
-    static constexpr int TMEM_COLS = (R * 2 * N <= 32) ? 32 : (R * 2 * N <= 64) ? 64 : (R * 2 * N <= 128) ? 128 : (R * 2 * N <= 256) ? 256 : 512;
+    static constexpr int BUDGET = 220 * 1024;
+    static constexpr int REST = BUDGET - CTRL_FLOATS * 4 - RAW_STAGES * RAW_STAGE * 4;
+    static constexpr int STAGES = (STAGE * 4 * 4 <= REST) ? 4 : ((STAGE * 4 * 3 <= REST) ? 3 : 2);
+    static constexpr size_t BYTES = (size_t)(STAGES * STAGE + RAW_STAGES * RAW_STAGE + CTRL_FLOATS) * 4;
+    static constexpr int ACC_COLS = R * 2 * N;  // TMEM columns of one accumulator set
+    static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
+    static_assert(2 * ACC_COLS <= 512, "two accumulator sets must fit the 512 TMEM columns");
 };
 
+// Persistent, warp-specialised implicit-GEMM convolution.  Four rings of mbarriers:
+//   raw  : loader -> transformers   (raw fp32 rows, bulk-copied RAW_STAGES chunks ahead: hides DRAM/L2 latency)
+//   ab   : transformers (+ weight bulk copy) -> MMA   (TF32 hi/lo A tile + [w_hi ; w_lo] B tile)
+//   acc  : MMA -> epilogue   (two TMEM accumulator sets: the epilogue of tile i overlaps the MMAs of tile i+1)
 template <int N, int R, int PAD, bool AFFINE>
-__global__ void __launch_bounds__(TC_THREADS, (N <= 32) ? 2 : 1) conv3x3_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
     using SM = TcSmem<N, R>;
     constexpr int TROWS = SM::TROWS;
     constexpr int S = SM::STAGES;
+    constexpr int RS = SM::RAW_STAGES;
     extern __shared__ __align__(128) float smem[];
-    // control block at the front (2 KB), stages after it
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);       // [S]
-    uint64_t* empty_bar = full_bar + 4;                           // [S]
-    uint64_t* accum_bar = full_bar + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 9);
-    float* sc_s = smem + 32;   // [<=128]
-    float* sh_s = smem + 160;  // [<=128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* ab_full = bars;            // [4]
+    uint64_t* ab_empty = bars + 4;       // [4]
+    uint64_t* raw_full = bars + 8;       // [4]
+    uint64_t* raw_empty = bars + 12;     // [4]
+    uint64_t* acc_full = bars + 16;      // [2]
+    uint64_t* acc_empty = bars + 18;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    float* sc_s = smem + 64;    // [<=128]
+    float* sh_s = smem + 192;   // [<=128]
     float* stage0 = smem + SM::CTRL_FLOATS;
+    float* raw0 = stage0 + (size_t)S * SM::STAGE;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = a.H, W = a.W, K = a.K;
-    const int tiles_x = W / 128;
-    const int x0 = (blockIdx.x % tiles_x) * 128;
-    const int y0 = (blockIdx.x / tiles_x) * R;
-    const int b = blockIdx.y;
     const size_t plane = (size_t)H * W;
-    const float* in_b = a.in + (size_t)b * K * plane;
     const int nchunks = K / TC_KC;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar + s, TC_PRODUCERS + 1);
-            mbar_init(empty_bar + s, 1);
-        }
-        mbar_init(accum_bar, 1);
+        for (int s = 0; s < S; ++s) { mbar_init(ab_full + s, TC_XF_THREADS + 1); mbar_init(ab_empty + s, 1); }
+        for (int s = 0; s < RS; ++s) { mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, TC_XF_THREADS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, TC_EPI_WARPS * 32); }
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, SM::TMEM_COLS);
+    if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, SM::TMEM_COLS);
     if (AFFINE) {
-        for (int i = tid; i < K; i += TC_THREADS) { sc_s[i] = __ldg(a.in_scale + i); sh_s[i] = __ldg(a.in_shift + i); }
+        for (int i = tid; i < K; i += TC_THREADS2) { sc_s[i] = __ldg(a.in_scale + i); sh_s[i] = __ldg(a.in_shift + i); }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 8) {
-        // =============================== producers: stage A (and kick the weight bulk copy) ===============================
-        // Each thread owns NIT fixed (channel quad, tile row, pixel) items.  All 4*NIT global loads of a chunk are issued
-        // before anything is consumed, and the loads of chunk ch+1 are in flight while chunk ch is split and stored.
-        constexpr int ITEMS = 2 * TROWS * TC_PITCH;
-        constexpr int NIT = (ITEMS + TC_PRODUCERS - 1) / TC_PRODUCERS;
-        int goff[NIT];   // pixel offset inside a channel plane, -1: zero-filled / unused item
-        int cq[NIT];     // channel quad (0/1) of the item
-#pragma unroll
-        for (int i = 0; i < NIT; ++i) {
-            const int it = tid + i * TC_PRODUCERS;
-            goff[i] = -1; cq[i] = 0;
-            if (it < ITEMS) {
-                const int q = it / (TROWS * TC_PITCH);
-                const int rem = it - q * (TROWS * TC_PITCH);
-                const int rr = rem / TC_PITCH, px = rem - rr * TC_PITCH;
-                int gy = y0 + rr - 1, gx = x0 + px - 1;
-                bool ok = true;
-                if (PAD == 0) {
-                    gy = min(max(gy, 0), H - 1);
-                    gx = min(max(gx, 0), W - 1);
-                } else {
-                    ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    auto tile_coords = [&](int tile, int& b, int& y0, int& x0) {
+        b = tile / tiles_per_img;
+        const int t = tile - b * tiles_per_img;
+        const int ty = t / a.tiles_x;
+        y0 = ty * R;
+        x0 = (t - ty * a.tiles_x) * 128;
+    };
+
+    if (warp == TC_LOAD_WARP) {
+        // ======================= loader: one TMA box (8 ch x TROWS rows x 136 cols) per chunk, RAW_STAGES ahead =======================
+        // Out-of-image elements are zero-filled by the TMA unit: exactly the zero padding of the data-gradient form;
+        // for replicate padding the transformers re-index them onto the clamped row / column, which is inside the box.
+        int g = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            int b, y0, x0;
+            tile_coords(tile, b, y0, x0);
+            for (int ch = 0; ch < nchunks; ++ch, ++g) {
+                const int rs = g % RS;
+                if (g >= RS) mbar_wait(raw_empty + rs, ((g / RS) - 1) & 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(raw_full + rs, SM::RAW_STAGE * 4);
+                    tma_load_3d(raw0 + (size_t)rs * SM::RAW_STAGE, &tmap, x0 - 4, y0 - 1, b * K + ch * TC_KC, raw_full + rs);
                 }
-                cq[i] = q;
-                goff[i] = ok ? gy * W + gx : -1;
+                __syncwarp();
             }
         }
-        float v[NIT][4], vn[NIT][4];
-        auto load_chunk = [&](int ch, float (&dst)[NIT][4]) {
-#pragma unroll
-            for (int i = 0; i < NIT; ++i) {
-                const float* src = in_b + (size_t)(ch * TC_KC + 4 * cq[i]) * plane + (goff[i] >= 0 ? goff[i] : 0);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) dst[i][e] = goff[i] >= 0 ? __ldg(src + (size_t)e * plane) : 0.f;
-            }
-        };
-        load_chunk(0, v);
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int s = ch % S;
-            float* a_hi = stage0 + (size_t)s * SM::STAGE;
-            float* a_lo = a_hi + SM::A_TILE;
-            float* b_st = a_lo + SM::A_TILE;
-            if (ch + 1 < nchunks) load_chunk(ch + 1, vn);
-            if (ch >= S) mbar_wait(empty_bar + s, ((ch / S) - 1) & 1);
-            if (tid == 0) {
-                mbar_arrive_expect_tx(full_bar + s, SM::B_TILE * 4);
-                bulk_g2s(b_st, a.wprep + (size_t)ch * SM::B_TILE, SM::B_TILE * 4, full_bar + s);
-            }
-            const int c0 = ch * TC_KC;
-#pragma unroll
-            for (int i = 0; i < NIT; ++i) {
-                const int it = tid + i * TC_PRODUCERS;
-                if (it < ITEMS) {
-                    float hi[4], lo[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float t = v[i][e];
-                        if (AFFINE && goff[i] >= 0) t = sifnn::act_affine_relu(t, sc_s[c0 + 4 * cq[i] + e], sh_s[c0 + 4 * cq[i] + e]);
-                        hi[e] = tf32_hi(t);
-                        lo[e] = t - hi[e];
-                    }
-                    *reinterpret_cast<float4*>(a_hi + (size_t)it * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(a_lo + (size_t)it * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                }
-            }
-            fence_proxy_async();  // generic-proxy st.shared -> visible to the tensor core (async proxy)
-            mbar_arrive(full_bar + s);
-#pragma unroll
-            for (int i = 0; i < NIT; ++i)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v[i][e] = vn[i][e];
-        }
-    } else {
-        // =============================== MMA issuer (one thread) ===============================
+    } else if (warp == TC_MMA_WARP) {
+        // ======================= MMA issuer (one thread) =======================
         constexpr uint32_t idesc1 = make_idesc(128, 2 * N);  // a_hi x [w_hi ; w_lo]
         constexpr uint32_t idesc2 = make_idesc(128, N);      // a_lo x  w_hi
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int s = ch % S;
-            mbar_wait(full_bar + s, (ch / S) & 1);
+        int g = 0, it = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            if (it >= 2) mbar_wait(acc_empty + ab, ((it >> 1) - 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_hi = smem_u32(stage0 + (size_t)s * SM::STAGE);
-                const uint32_t a_lo = a_hi + SM::A_TILE * 4;
-                const uint32_t b_st = a_lo + SM::A_TILE * 4;
-                constexpr uint32_t LBO_A = TROWS * TC_PITCH * 16, LBO_B = 2 * N * 16, SBO = 128;
-#pragma unroll 1
-                for (int r = 0; r < R; ++r) {
+            for (int ch = 0; ch < nchunks; ++ch, ++g) {
+                const int s = g % S;
+                mbar_wait(ab_full + s, (g / S) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    // The issuing thread is the critical path of the whole CTA (72 MMAs per chunk from ONE thread), so the
+                    // descriptors are built once per stage and advanced by compile-time constants: the start-address field
+                    // is the low 14 bits in 16-byte units, and every offset below stays inside the 256 KB window.
+                    constexpr uint32_t LBO_A = TROWS * TC_PITCH * 16, LBO_B = 2 * N * 16, SBO = 128;
+                    const uint32_t a_hi = smem_u32(stage0 + (size_t)s * SM::STAGE);
+                    const uint64_t da_hi = make_desc(a_hi, LBO_A, SBO);
+                    const uint64_t da_lo = da_hi + (uint64_t)(SM::A_TILE * 4 / 16);
+                    const uint64_t db = da_hi + (uint64_t)(2 * SM::A_TILE * 4 / 16) - ((uint64_t)(LBO_A >> 4) << 16) + ((uint64_t)(LBO_B >> 4) << 16);
+                    const uint32_t first = (ch != 0) ? 1u : 0u;
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const int ky = t / 3, kx = t - 3 * ky;
-                        const uint32_t aoff = ((r + ky) * TC_PITCH + kx) * 16;
-                        const uint64_t db = make_desc(b_st + t * (2 * 2 * N * 16), LBO_B, SBO);
-                        const uint32_t d = tmem_base + r * 2 * N;
-                        if (a.dbg == 1) continue;
-                        umma_tf32(d, make_desc(a_hi + aoff, LBO_A, SBO), db, idesc1, (ch | t) != 0);
-                        umma_tf32(d, make_desc(a_lo + aoff, LBO_A, SBO), db, idesc2, 1);
-                        if (a.dbg == 2) {
-                            umma_tf32(d, make_desc(a_hi + aoff, LBO_A, SBO), db, idesc1, 1);
-                            umma_tf32(d, make_desc(a_lo + aoff, LBO_A, SBO), db, idesc2, 1);
+                    for (int r = 0; r < R; ++r) {
+                        const uint32_t d = tmem_base + ab * SM::ACC_COLS + r * 2 * N;
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            const int ky = t / 3, kx = t - 3 * ky;
+                            const uint64_t oa = (uint64_t)((r + ky) * TC_PITCH + kx);  // 16-byte units
+                            const uint64_t ob = (uint64_t)(t * 2 * 2 * N);
+                            umma_tf32(d, da_hi + oa, db + ob, idesc1, t == 0 ? first : 1u);
+                            umma_tf32(d, da_lo + oa, db + ob, idesc2, 1u);
                         }
                     }
+                    umma_commit(ab_empty + s);                        // stage reusable once these MMAs have read it
+                    if (ch == nchunks - 1) umma_commit(acc_full + ab);  // accumulator set complete
                 }
-                umma_commit(empty_bar + s);                       // stage free once these MMAs have read it
-                if (ch == nchunks - 1) umma_commit(accum_bar);    // accumulators complete
+                __syncwarp();
             }
-            __syncwarp();
         }
-    }
-
-    // =============================== epilogue: TMEM -> registers -> global ===============================
-    if (warp < 8) {
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const int quad = warp & 3, half = warp >> 2;       // TMEM lane quadrant this warp may read; channel half it handles
-        const int x = x0 + quad * 32 + lane;
+    } else if (warp >= TC_XF_WARP0) {
+        // ======================= transformers: raw -> BN/ReLU -> TF32 hi/lo pixel-major tiles =======================
+        const int xt = tid - TC_XF_WARP0 * 32;
+        constexpr int ITEMS = 2 * TROWS * TC_PITCH;
+        constexpr int NIT = (ITEMS + TC_XF_THREADS - 1) / TC_XF_THREADS;
+        int g = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            int b, y0, x0;
+            tile_coords(tile, b, y0, x0);
+            const int jlo = (x0 == 0) ? 4 : 3, jhi = (x0 + 128 >= W) ? 131 : 132;  // staged columns that exist in the image
+            for (int ch = 0; ch < nchunks; ++ch, ++g) {
+                const int s = g % S, rs = g % RS;
+                float* a_hi = stage0 + (size_t)s * SM::STAGE;
+                float* a_lo = a_hi + SM::A_TILE;
+                const float* raw = raw0 + (size_t)rs * SM::RAW_STAGE;
+                if (g >= S) mbar_wait(ab_empty + s, ((g / S) - 1) & 1);
+                if (xt == 0) {  // weights of this chunk: one bulk copy straight into the stage
+                    mbar_arrive_expect_tx(ab_full + s, SM::B_TILE * 4);
+                    bulk_g2s(a_lo + SM::A_TILE, a.wprep + (size_t)ch * SM::B_TILE, SM::B_TILE * 4, ab_full + s);
+                }
+                mbar_wait(raw_full + rs, (g / RS) & 1);
+                const int c0 = ch * TC_KC;
+#pragma unroll
+                for (int i = 0; i < NIT; ++i) {
+                    const int item = xt + i * TC_XF_THREADS;
+                    if (item < ITEMS) {
+                        const int q = item / (TROWS * TC_PITCH);
+                        const int rem = item - q * (TROWS * TC_PITCH);
+                        const int rr = rem / TC_PITCH, px = rem - rr * TC_PITCH;
+                        int j = px + 3, rj = rr;
+                        if (PAD == 0) {  // replicate: clamp onto the image; the clamped element is inside the staged box
+                            j = min(max(j, jlo), jhi);
+                            rj = min(max(y0 + rr - 1, 0), H - 1) - (y0 - 1);
+                        }
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float t = raw[((4 * q + e) * TROWS + rj) * TC_RAW_ROW + j];
+                            if (AFFINE) t = sifnn::act_affine_relu(t, sc_s[c0 + 4 * q + e], sh_s[c0 + 4 * q + e]);
+                            hi[e] = tf32_hi(t);
+                            lo[e] = t - hi[e];
+                        }
+                        *reinterpret_cast<float4*>(a_hi + (size_t)item * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4*>(a_lo + (size_t)item * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+                mbar_arrive(raw_empty + rs);   // raw slot consumed (generic-proxy reads done)
+                fence_proxy_async();           // st.shared -> visible to the tensor core (async proxy)
+                mbar_arrive(ab_full + s);
+            }
+        }
+    } else {
+        // ======================= epilogue: TMEM -> registers -> global (+ BatchNorm statistics) =======================
+        const int quad = warp & 3, half = warp >> 2;
         constexpr int NH = N / 2;
         float s1[NH], s2[NH];
 #pragma unroll
         for (int j = 0; j < NH; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+            int b, y0, x0;
+            tile_coords(tile, b, y0, x0);
+            const int ab = it & 1;
+            mbar_wait(acc_full + ab, (it >> 1) & 1);
+            tc_fence_after();
+            const int x = x0 + quad * 32 + lane;
 #pragma unroll 1
-        for (int r = 0; r < R; ++r) {
-            const int y = y0 + r;
+            for (int r = 0; r < R; ++r) {
+                const int y = y0 + r;
 #pragma unroll
-            for (int n0 = 0; n0 < NH; n0 += 8) {
-                const int n = half * NH + n0;
-                float d1[8], d2[8];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + r * 2 * N + n;
-                tmem_ld8(taddr, d1);
-                tmem_ld8(taddr + N, d2);
-                tmem_ld_wait();
-                if (y < H) {
+                for (int n0 = 0; n0 < NH; n0 += 8) {
+                    const int n = half * NH + n0;
+                    float d1[8], d2[8];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ab * SM::ACC_COLS + r * 2 * N + n;
+                    tmem_ld8(taddr, d1);
+                    tmem_ld8(taddr + N, d2);
+                    tmem_ld_wait();
+                    if (y < H) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float v = d1[j] + d2[j];
-                        if (a.bias) v += __ldg(a.bias + n + j);
-                        float* op = a.out + ((size_t)b * a.O + n + j) * plane + (size_t)y * W + x;
-                        if (a.accumulate) v += *op;
-                        *op = v;
-                        s1[n0 + j] += v;
-                        s2[n0 + j] = fmaf(v, v, s2[n0 + j]);
+                        for (int j = 0; j < 8; ++j) {
+                            float v = d1[j] + d2[j];
+                            if (a.bias) v += __ldg(a.bias + n + j);
+                            float* op = a.out + ((size_t)b * a.O + n + j) * plane + (size_t)y * W + x;
+                            if (a.accumulate) v += *op;
+                            *op = v;
+                            s1[n0 + j] += v;
+                            s2[n0 + j] = fmaf(v, v, s2[n0 + j]);
+                        }
                     }
                 }
             }
+            tc_fence_before();
+            mbar_arrive(acc_empty + ab);   // this accumulator set may be overwritten by tile it + 2
         }
         if (a.stats) {
-            // per-channel sums over this CTA's pixels: lanes -> shuffle; 4 quadrant warps -> shared -> one atomic per channel
-            float* red = stage0;  // all MMAs have completed (accum_bar), the stages are dead: [8 warps][NH][2]
+            // per-channel sums over all pixels this CTA produced: lanes by shuffle, then one fp64 atomic per warp and channel
 #pragma unroll
             for (int j = 0; j < NH; ++j) {
                 const float t1 = sifnn::warp_sum(s1[j]), t2 = sifnn::warp_sum(s2[j]);
-                if (lane == 0) { red[(warp * NH + j) * 2] = t1; red[(warp * NH + j) * 2 + 1] = t2; }
+                if (lane == 0) {
+                    atomicAdd(a.stats + half * NH + j, (double)t1);
+                    atomicAdd(a.stats + a.O + half * NH + j, (double)t2);
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (a.stats && tid < N) {
-        constexpr int NH = N / 2;
-        const int half = tid / NH, j = tid - half * NH;
-        const float* red = stage0;
-        double d1 = 0.0, d2 = 0.0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            d1 += (double)red[((half * 4 + q) * NH + j) * 2];
-            d2 += (double)red[((half * 4 + q) * NH + j) * 2 + 1];
-        }
-        atomicAdd(a.stats + tid, d1);
-        atomicAdd(a.stats + a.O + tid, d2);
-    }
-    if (warp == 8) {
+    if (warp == TC_MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, SM::TMEM_COLS);
     }
@@ -371,8 +400,22 @@ __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __res
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
 template <int N, int R, int PAD, bool AFFINE>
-int launch_tc(const TcArgs& a, cudaStream_t st) {
+int launch_tc(const TcArgs& a0, cudaStream_t st) {
     using SM = TcSmem<N, R>;
     auto kern = conv3x3_tc_kernel<N, R, PAD, AFFINE>;
     static bool attr_done = false;
@@ -380,8 +423,23 @@ int launch_tc(const TcArgs& a, cudaStream_t st) {
         SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
         attr_done = true;
     }
-    dim3 grid((a.W / 128) * ((a.H + R - 1) / R), a.B);
-    kern<<<grid, TC_THREADS, SM::BYTES, st>>>(a);
+    TcArgs a = a0;
+    a.tiles_x = a.W / 128;
+    a.tiles_y = (a.H + R - 1) / R;
+    a.num_tiles = a.B * a.tiles_x * a.tiles_y;
+    // activation tensor as a 3-D TMA tensor {W, H, B*K planes}; box = {136 columns, R+2 rows, 8 planes}
+    EncodeTiledFn enc = get_encode_fn();
+    SIFNN_REQUIRE(enc != nullptr, "conv3x3_tc: cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B * a.K};
+    const cuuint64_t gstride[2] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.W * a.H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)TC_RAW_ROW, (cuuint32_t)(R + 2), (cuuint32_t)TC_KC};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.in), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SIFNN_REQUIRE(cr == CUDA_SUCCESS, "conv3x3_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    const int grid = a.num_tiles < sifnn::num_sms() ? a.num_tiles : sifnn::num_sms();  // persistent: one CTA per SM
+    kern<<<grid, TC_THREADS2, SM::BYTES, st>>>(a, tmap);
     return sifnn::check_launch("conv3x3_tc_kernel");
 }
 
@@ -396,9 +454,6 @@ int dispatch_tc(const TcArgs& a, cudaStream_t st) {
 }
 
 }  // namespace
-
-static int g_tc_dbg = 0;
-extern "C" void sifnn_tc_debug(int mode) { g_tc_dbg = mode; }
 
 extern "C" int sifnn_conv3x3_tc_supported(int Cin, int Cout, int H, int W) {
     return (W % 128 == 0) && (Cin % 8 == 0) && Cin <= 128 && (Cout == 16 || Cout == 32 || Cout == 64) && H >= 1;
@@ -417,7 +472,7 @@ extern "C" int sifnn_conv3x3_fwd_tc(const float* in, const float* in_scale, cons
     SIFNN_TRY(sifnn::check_launch("tc_prep_weights_kernel"));
     TcArgs a{};
     a.in = in; a.in_scale = in_scale; a.in_shift = in_shift; a.wprep = static_cast<const float*>(wprep); a.bias = bias; a.out = out; a.stats = stats;
-    a.B = B; a.K = Cin; a.O = Cout; a.H = H; a.W = W; a.accumulate = 0; a.dbg = g_tc_dbg;
+    a.B = B; a.K = Cin; a.O = Cout; a.H = H; a.W = W; a.accumulate = 0;
     return in_scale ? dispatch_tc<0, true>(a, st) : dispatch_tc<0, false>(a, st);
 }
 
@@ -432,6 +487,6 @@ extern "C" int sifnn_conv3x3_dgrad_tc_main(const float* dy, const float* w, floa
     SIFNN_TRY(sifnn::check_launch("tc_prep_weights_kernel"));
     TcArgs a{};
     a.in = dy; a.wprep = static_cast<const float*>(wprep); a.out = dx;
-    a.B = B; a.K = Cout; a.O = Cin; a.H = H; a.W = W; a.accumulate = accumulate ? 1 : 0; a.dbg = g_tc_dbg;
+    a.B = B; a.K = Cout; a.O = Cin; a.H = H; a.W = W; a.accumulate = accumulate ? 1 : 0;
     return dispatch_tc<1, false>(a, st);
 }

@@ -7,6 +7,7 @@
 // The caller owns the workspace; this file only carves it up.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -59,6 +60,16 @@ Net build_net(const sifnn_modelb_cfg* cfg) {
     return n;
 }
 
+// tcgen05 path on by default where the shape is eligible; SIFNN_DISABLE_TC=1 forces the fp32 SIMT kernels everywhere
+bool tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SIFNN_DISABLE_TC");
+        v = (e && e[0] && e[0] != '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 struct Carver {
     char* base;
     size_t off;
@@ -84,6 +95,7 @@ struct Workspace {
     float* gR[3];
     float* gU[3];
     void* wgrad_ws;
+    void* wprep;  // hi/lo-split weights of the convolution in flight (tensor-core path)
     size_t bytes;
 };
 
@@ -105,6 +117,16 @@ Workspace carve(const Net& n, void* base, int B, int H, int W, int train) {
     w.invstd = c.take<float>(n.bn_total);
     w.stats = c.take<double>(2 * n.bn_total);
     w.bsums = c.take<double>(2 * n.bn_total);
+    {
+        size_t mx = 0;
+        for (int i = 0; i < SIFNN_MODELB_NCONV; ++i) {
+            const size_t b = sifnn_conv3x3_tc_wprep_bytes((n.conv[i].cin + 7) / 8 * 8, n.conv[i].cout);
+            const size_t b2 = sifnn_conv3x3_tc_wprep_bytes((n.conv[i].cout + 7) / 8 * 8, n.conv[i].cin);
+            if (b > mx) mx = b;
+            if (b2 > mx) mx = b2;
+        }
+        w.wprep = c.take<char>(mx);
+    }
     if (train) {
         for (int i = 0; i < SIFNN_MODELB_NBN; ++i) w.g[i] = c.take<float>((size_t)B * n.conv[i].cout * hw[n.conv[i].level]);
         for (int k = 0; k < 3; ++k) w.gR[k] = c.take<float>((size_t)B * n.d[k] * hw[k + 1]);
@@ -193,9 +215,16 @@ extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* pa
         const ConvDesc& c = n.conv[i];
         const int l = c.level;
         const bool bn = i < SIFNN_MODELB_NBN;
-        SIFNN_TRY(sifnn_conv3x3_fwd(in, aff >= 0 ? w.scale + n.bn_off[aff] : nullptr, aff >= 0 ? w.shift + n.bn_off[aff] : nullptr,
-                                    params + n.w_off[i], bn ? nullptr : params + n.bias_off, out,
-                                    (bn && train) ? w.stats + 2 * n.bn_off[i] : nullptr, B, c.cin, c.cout, hs[l], ws[l], stream));
+        const float* isc = aff >= 0 ? w.scale + n.bn_off[aff] : nullptr;
+        const float* ish = aff >= 0 ? w.shift + n.bn_off[aff] : nullptr;
+        double* st_ptr = (bn && train) ? w.stats + 2 * n.bn_off[i] : nullptr;
+        if (tc_enabled() && sifnn_conv3x3_tc_supported(c.cin, c.cout, hs[l], ws[l])) {
+            SIFNN_TRY(sifnn_conv3x3_fwd_tc(in, isc, ish, params + n.w_off[i], bn ? nullptr : params + n.bias_off, out, st_ptr, w.wprep, B, c.cin,
+                                           c.cout, hs[l], ws[l], stream));
+        } else {
+            SIFNN_TRY(sifnn_conv3x3_fwd(in, isc, ish, params + n.w_off[i], bn ? nullptr : params + n.bias_off, out, st_ptr, B, c.cin, c.cout, hs[l],
+                                        ws[l], stream));
+        }
         if (bn && train) {
             const int64_t o = n.bn_off[i];
             SIFNN_TRY(sifnn_bn_train_finalize(w.stats + 2 * o, params + n.gamma_off[i], params + n.beta_off[i], running_mean + o, running_var + o,
@@ -250,6 +279,8 @@ extern "C" int sifnn_modelb_backward(const sifnn_modelb_cfg* cfg, const float* p
     };
     auto dgrad = [&](int i, const float* g, float* dx, int accumulate) -> int {
         const ConvDesc& c = n.conv[i];
+        if (tc_enabled() && sifnn_conv3x3_tc_supported(c.cout, c.cin, hs[c.level], ws[c.level]))
+            return sifnn_conv3x3_dgrad_tc(g, params + n.w_off[i], dx, accumulate, w.wprep, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
         return sifnn_conv3x3_dgrad(g, params + n.w_off[i], dx, accumulate, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
     };
     // BatchNorm+ReLU backward of layer i: dY (gradient w.r.t. the activated output) -> dx (w.r.t. raw[i])

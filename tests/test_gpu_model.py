@@ -166,13 +166,22 @@ def test_autograd_dropin_step_vs_golden(kind):
     grads = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
     assert grads.numel() == 282705
     assert rel_err(grads, g["grads"]) < TOL
-    # per-tensor check as well: every one of the 53 gradients within 1e-4 of its own max
-    off = 0
+    # per-tensor check as well.  Some tensors (conv weights feeding a BatchNorm) have gradients that are pure
+    # cancellation residue, 1e-5 of the others: there the reference's own fp32 result is noise-limited, so the
+    # yardstick is the oracle in fp64 and the bar "within 1e-4 of the tensor's max, or no worse than 10x the
+    # reference's own fp32 error on that tensor".
+    ref64 = O.Trainer(load_ckpt("1009"), kind, alpha, gamma, lr, dtype=torch.float64)
+    ref64.loss_and_grads(*syn_inputs())
+    g64 = ref64.flat_grads()
+    off, worst = 0, (0.0, "")
     for name, p in m.named_parameters():
         n = p.numel()
-        ref = g["grads"][off:off + n]
-        assert rel_err(p.grad.reshape(-1), ref) < 5e-4, name
+        e_ours = rel_err(p.grad.reshape(-1), g64[off:off + n])
+        e_ref = rel_err(g["grads"][off:off + n], g64[off:off + n])
+        assert e_ours <= max(1e-4, 10 * e_ref), (name, e_ours, e_ref)
+        worst = max(worst, (e_ours, name))
         off += n
+    print("\nworst per-tensor gradient rel.err vs fp64: %.2e (%s)" % worst)
     opt.step()
     if "params_after" in g:
         params = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
