@@ -175,6 +175,11 @@ typedef struct {
 #define SIFNN_MODELB_NCONV 18
 #define SIFNN_MODELB_NBN 17
 
+/* Whether the whole-network entry points may use the tcgen05 kernels on eligible layers (default 1, or 0 when the
+ * environment variable SIFNN_DISABLE_TC is set).  0 = "strict fp32": SIMT kernels everywhere. */
+void sifnn_set_tensor_cores(int on);
+int sifnn_get_tensor_cores(void);
+
 /* Offsets (in floats) of every tensor inside the flat parameter buffer, in
  * module.parameters() order: conv weight, then (gamma, beta) per BatchNorm layer; outlay
  * weight, outlay bias.  w_off[18], gamma_off[17], beta_off[17]; returns total floats

@@ -15,4 +15,15 @@ from .losses import sr_losses, sr1_losses, sr2_losses, loss_fwd_bwd  # noqa: F40
 from .trainer import Trainer  # noqa: F401
 from .parallel import block_partition, shard_batch, BucketedAllReduce  # noqa: F401
 
+
+
+def set_tensor_cores(on: bool) -> None:
+    """Allow (default) or forbid the tcgen05 kernels in ModelB_2 / Trainer.  ``False`` = strict fp32 SIMT everywhere."""
+    load().sifnn_set_tensor_cores(1 if on else 0)
+
+
+def tensor_cores_enabled() -> bool:
+    return bool(load().sifnn_get_tensor_cores())
+
+
 __version__ = "0.1.0"

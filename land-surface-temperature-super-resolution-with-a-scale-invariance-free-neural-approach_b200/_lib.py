@@ -86,6 +86,8 @@ SIGNATURES = {
     "sifnn_loss_fwd_bwd": (c_int, [c_int] + [c_void_p] * 7 + [c_float, c_float] + [c_void_p] * 2 + [c_int] * 3 + [c_void_p]),
     "sifnn_adam_step": (c_int, [c_void_p] * 5 + [c_double] * 4 + [c_float, c_int64, c_void_p]),
     "sifnn_fp32_peak_kernel": (c_int, [c_void_p, c_int, _d, c_void_p]),
+    "sifnn_set_tensor_cores": (None, [c_int]),
+    "sifnn_get_tensor_cores": (c_int, []),
     "sifnn_modelb_param_layout": (c_int64, [POINTER(ModelBCfg)] + [POINTER(c_int64)] * 6),
     "sifnn_modelb_workspace_bytes": (c_size_t, [POINTER(ModelBCfg), c_int, c_int, c_int, c_int]),
     "sifnn_modelb_forward": (c_int, [POINTER(ModelBCfg)] + [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),

@@ -60,14 +60,15 @@ Net build_net(const sifnn_modelb_cfg* cfg) {
     return n;
 }
 
-// tcgen05 path on by default where the shape is eligible; SIFNN_DISABLE_TC=1 forces the fp32 SIMT kernels everywhere
+// tcgen05 path on by default where the shape is eligible; SIFNN_DISABLE_TC=1 (or sifnn_set_tensor_cores(0)) forces the
+// fp32 SIMT kernels everywhere ("strict fp32" mode: no tensor-core accumulation rounding).
+int g_tc_mode = -1;
 bool tc_enabled() {
-    static int v = -1;
-    if (v < 0) {
+    if (g_tc_mode < 0) {
         const char* e = getenv("SIFNN_DISABLE_TC");
-        v = (e && e[0] && e[0] != '0') ? 0 : 1;
+        g_tc_mode = (e && e[0] && e[0] != '0') ? 0 : 1;
     }
-    return v == 1;
+    return g_tc_mode == 1;
 }
 
 struct Carver {
@@ -165,6 +166,9 @@ __global__ void bn_eval_affine_all_kernel(const float* __restrict__ params, cons
 bool shape_ok(int B, int H, int W) { return B > 0 && B <= 65535 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0; }
 
 }  // namespace
+
+extern "C" void sifnn_set_tensor_cores(int on) { g_tc_mode = on ? 1 : 0; }
+extern "C" int sifnn_get_tensor_cores(void) { return tc_enabled() ? 1 : 0; }
 
 extern "C" int64_t sifnn_modelb_param_layout(const sifnn_modelb_cfg* cfg, int64_t* w_off, int64_t* gamma_off, int64_t* beta_off,
                                              int64_t* bias_off, int64_t* bn_off, int64_t* bn_total) {
