@@ -24,7 +24,6 @@
 
 namespace {
 
-constexpr int TC_PITCH = 130;      // 128 pixels + 2 halo columns
 constexpr int TC_KC = 8;           // channels per pipeline stage = one MMA K step (TF32: 32 bytes)
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -136,15 +135,17 @@ constexpr int TC_MMA_WARP = 9;      // warp 9     : issues tcgen05.mma / tcgen05
 constexpr int TC_XF_WARP0 = 10;     // warps 10..17: transform raw rows -> (BatchNorm, ReLU) -> TF32 hi/lo pixel-major tiles
 constexpr int TC_XF_THREADS = 256;
 constexpr int TC_THREADS2 = (TC_XF_WARP0 + 8) * 32;
-constexpr int TC_RAW_ROW = 136;     // floats per staged raw row: gx = x0-4 .. x0+131 (16-byte aligned both ends)
 
-template <int N, int R>
+// N = output channels, R = output rows per tile, MM = pixels per MMA (the UMMA M: 128, or 64 for 64-pixel-wide images)
+template <int N, int R, int MM>
 struct TcSmem {
     static constexpr int TROWS = R + 2;
-    static constexpr int A_TILE = 2 * TROWS * TC_PITCH * 4;  // floats per (hi or lo) tile: [2 q][TROWS*PITCH px][4]
+    static constexpr int PITCH = MM + 2;        // tile row: MM pixels + 2 halo columns
+    static constexpr int RAW_ROW = MM + 8;      // staged raw row: gx = x0-4 .. x0+MM+3 (16-byte aligned both ends)
+    static constexpr int A_TILE = 2 * TROWS * PITCH * 4;  // floats per (hi or lo) tile: [2 q][TROWS*PITCH px][4]
     static constexpr int B_TILE = 9 * 2 * 2 * N * 4;          // floats: [9 taps][2 q][2N rows][4]
     static constexpr int STAGE = 2 * A_TILE + B_TILE;
-    static constexpr int RAW_STAGE = TC_KC * TROWS * TC_RAW_ROW;  // floats
+    static constexpr int RAW_STAGE = TC_KC * TROWS * RAW_ROW;  // floats
     static constexpr int RAW_STAGES = 3;
     static constexpr int CTRL_FLOATS = 512;  // barriers, TMEM slot, BatchNorm scale/shift (2 KB)
     static constexpr int BUDGET = 220 * 1024;
@@ -154,16 +155,21 @@ struct TcSmem {
     static constexpr int ACC_COLS = R * 2 * N;  // TMEM columns of one accumulator set
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
     static_assert(2 * ACC_COLS <= 512, "two accumulator sets must fit the 512 TMEM columns");
+    static_assert((STAGE * 4) % 128 == 0 && (RAW_STAGE * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(2 * N <= 256, "UMMA N limit");
 };
 
 // Persistent, warp-specialised implicit-GEMM convolution.  Four rings of mbarriers:
 //   raw  : loader -> transformers   (raw fp32 rows, bulk-copied RAW_STAGES chunks ahead: hides DRAM/L2 latency)
 //   ab   : transformers (+ weight bulk copy) -> MMA   (TF32 hi/lo A tile + [w_hi ; w_lo] B tile)
 //   acc  : MMA -> epilogue   (two TMEM accumulator sets: the epilogue of tile i overlaps the MMAs of tile i+1)
-template <int N, int R, int PAD, bool AFFINE>
+template <int N, int R, int MM, int PAD, bool AFFINE>
 __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
-    using SM = TcSmem<N, R>;
+    using SM = TcSmem<N, R, MM>;
     constexpr int TROWS = SM::TROWS;
+    constexpr int TC_PITCH = SM::PITCH;
+    constexpr int TC_RAW_ROW = SM::RAW_ROW;
+    constexpr bool STATS = (PAD == 0);  // BatchNorm statistics exist only in the forward (replicate) form
     constexpr int S = SM::STAGES;
     constexpr int RS = SM::RAW_STAGES;
     extern __shared__ __align__(128) float smem[];
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
         const int t = tile - b * tiles_per_img;
         const int ty = t / a.tiles_x;
         y0 = ty * R;
-        x0 = (t - ty * a.tiles_x) * 128;
+        x0 = (t - ty * a.tiles_x) * MM;
     };
 
     if (warp == TC_LOAD_WARP) {
@@ -229,8 +235,8 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
         }
     } else if (warp == TC_MMA_WARP) {
         // ======================= MMA issuer (one thread) =======================
-        constexpr uint32_t idesc1 = make_idesc(128, 2 * N);  // a_hi x [w_hi ; w_lo]
-        constexpr uint32_t idesc2 = make_idesc(128, N);      // a_lo x  w_hi
+        constexpr uint32_t idesc1 = make_idesc(MM, 2 * N);  // a_hi x [w_hi ; w_lo]
+        constexpr uint32_t idesc2 = make_idesc(MM, N);      // a_lo x  w_hi
         int g = 0, it = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
@@ -280,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             int b, y0, x0;
             tile_coords(tile, b, y0, x0);
-            const int jlo = (x0 == 0) ? 4 : 3, jhi = (x0 + 128 >= W) ? 131 : 132;  // staged columns that exist in the image
+            const int jlo = (x0 == 0) ? 4 : 3, jhi = (x0 + MM >= W) ? MM + 3 : MM + 4;  // staged columns that exist in the image
             for (int ch = 0; ch < nchunks; ++ch, ++g) {
                 const int s = g % S, rs = g % RS;
                 float* a_hi = stage0 + (size_t)s * SM::STAGE;
@@ -324,11 +330,15 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
         }
     } else {
         // ======================= epilogue: TMEM -> registers -> global (+ BatchNorm statistics) =======================
+        // M = 128: accumulator row m lives in TMEM lane m.  M = 64: row m lives in lane (m % 16) + 32 * (m / 16), i.e. the
+        // lower 16 lanes of each quadrant (cute "half subpartitions" atom), so only lanes 0..15 of a warp carry pixels.
         const int quad = warp & 3, half = warp >> 2;
         constexpr int NH = N / 2;
-        float s1[NH], s2[NH];
+        constexpr int LANES = (MM == 128) ? 32 : 16;
+        const bool lane_ok = lane < LANES;
+        float s1[STATS ? NH : 1], s2[STATS ? NH : 1];
 #pragma unroll
-        for (int j = 0; j < NH; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+        for (int j = 0; j < (STATS ? NH : 1); ++j) { s1[j] = 0.f; s2[j] = 0.f; }
         int it = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
             int b, y0, x0;
@@ -336,7 +346,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
             const int ab = it & 1;
             mbar_wait(acc_full + ab, (it >> 1) & 1);
             tc_fence_after();
-            const int x = x0 + quad * 32 + lane;
+            const int x = x0 + quad * LANES + lane;
 #pragma unroll 1
             for (int r = 0; r < R; ++r) {
                 const int y = y0 + r;
@@ -348,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
                     tmem_ld8(taddr, d1);
                     tmem_ld8(taddr + N, d2);
                     tmem_ld_wait();
-                    if (y < H) {
+                    if (y < H && lane_ok) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float v = d1[j] + d2[j];
@@ -356,8 +366,10 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
                             float* op = a.out + ((size_t)b * a.O + n + j) * plane + (size_t)y * W + x;
                             if (a.accumulate) v += *op;
                             *op = v;
-                            s1[n0 + j] += v;
-                            s2[n0 + j] = fmaf(v, v, s2[n0 + j]);
+                            if (STATS) {
+                                s1[n0 + j] += v;
+                                s2[n0 + j] = fmaf(v, v, s2[n0 + j]);
+                            }
                         }
                     }
                 }
@@ -365,10 +377,10 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
             tc_fence_before();
             mbar_arrive(acc_empty + ab);   // this accumulator set may be overwritten by tile it + 2
         }
-        if (a.stats) {
+        if (STATS && a.stats) {
             // per-channel sums over all pixels this CTA produced: lanes by shuffle, then one fp64 atomic per warp and channel
 #pragma unroll
-            for (int j = 0; j < NH; ++j) {
+            for (int j = 0; j < (STATS ? NH : 1); ++j) {
                 const float t1 = sifnn::warp_sum(s1[j]), t2 = sifnn::warp_sum(s2[j]);
                 if (lane == 0) {
                     atomicAdd(a.stats + half * NH + j, (double)t1);
@@ -417,17 +429,17 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int N, int R, int PAD, bool AFFINE>
+template <int N, int R, int MM, int PAD, bool AFFINE>
 int launch_tc(const TcArgs& a0, cudaStream_t st) {
-    using SM = TcSmem<N, R>;
-    auto kern = conv3x3_tc_kernel<N, R, PAD, AFFINE>;
+    using SM = TcSmem<N, R, MM>;
+    auto kern = conv3x3_tc_kernel<N, R, MM, PAD, AFFINE>;
     static bool attr_done = false;
     if (!attr_done) {
         SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
         attr_done = true;
     }
     TcArgs a = a0;
-    a.tiles_x = a.W / 128;
+    a.tiles_x = a.W / MM;
     a.tiles_y = (a.H + R - 1) / R;
     a.num_tiles = a.B * a.tiles_x * a.tiles_y;
     // activation tensor as a 3-D TMA tensor {W, H, B*K planes}; box = {136 columns, R+2 rows, 8 planes}
@@ -436,7 +448,7 @@ int launch_tc(const TcArgs& a0, cudaStream_t st) {
     CUtensorMap tmap;
     const cuuint64_t gdim[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B * a.K};
     const cuuint64_t gstride[2] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.W * a.H * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)TC_RAW_ROW, (cuuint32_t)(R + 2), (cuuint32_t)TC_KC};
+    const cuuint32_t box[3] = {(cuuint32_t)SM::RAW_ROW, (cuuint32_t)(R + 2), (cuuint32_t)TC_KC};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.in), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -448,18 +460,29 @@ int launch_tc(const TcArgs& a0, cudaStream_t st) {
 
 template <int PAD, bool AFFINE>
 int dispatch_tc(const TcArgs& a, cudaStream_t st) {
-    switch (a.O) {
-        case 16: return launch_tc<16, 2, PAD, AFFINE>(a, st);
-        case 32: return launch_tc<32, 2, PAD, AFFINE>(a, st);
-        case 64: return launch_tc<64, 2, PAD, AFFINE>(a, st);
-        default: sifnn::set_error("conv3x3_tc: unsupported channel count %d", a.O); return SIFNN_EINVAL;
+    if (a.W % 128 == 0) {
+        switch (a.O) {
+            case 16: return launch_tc<16, 2, 128, PAD, AFFINE>(a, st);
+            case 32: return launch_tc<32, 2, 128, PAD, AFFINE>(a, st);
+            case 64: return launch_tc<64, 2, 128, PAD, AFFINE>(a, st);
+        }
+    } else {  // 64-pixel-wide images: one image row per M = 64 MMA
+        switch (a.O) {
+            case 16: return launch_tc<16, 4, 64, PAD, AFFINE>(a, st);
+            case 32: return launch_tc<32, 4, 64, PAD, AFFINE>(a, st);
+            case 64: return launch_tc<64, 2, 64, PAD, AFFINE>(a, st);
+            case 128: if constexpr (PAD == 1 && !AFFINE) return launch_tc<128, 1, 64, PAD, AFFINE>(a, st); else break;
+        }
     }
+    sifnn::set_error("conv3x3_tc: unsupported channel count %d", a.O);
+    return SIFNN_EINVAL;
 }
 
 }  // namespace
 
 extern "C" int sifnn_conv3x3_tc_supported(int Cin, int Cout, int H, int W) {
-    return (W % 128 == 0) && (Cin % 8 == 0) && Cin <= 128 && (Cout == 16 || Cout == 32 || Cout == 64) && H >= 1;
+    // 128 output channels (the data gradient of ub1's first convolution) only in the 64-pixel-wide form: the stage would not fit otherwise
+    return (W % 64 == 0) && (Cin % 8 == 0) && Cin <= 128 && (Cout == 16 || Cout == 32 || Cout == 64 || (Cout == 128 && W % 128 != 0)) && H >= 1;
 }
 
 extern "C" size_t sifnn_conv3x3_tc_wprep_bytes(int Cin, int Cout) { return (size_t)(Cin / 8) * 9 * 2 * 2 * Cout * 4 * sizeof(float); }
@@ -467,6 +490,7 @@ extern "C" size_t sifnn_conv3x3_tc_wprep_bytes(int Cin, int Cout) { return (size
 extern "C" int sifnn_conv3x3_fwd_tc(const float* in, const float* in_scale, const float* in_shift, const float* w, const float* bias,
                                     float* out, double* stats, void* wprep, int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream) {
     SIFNN_REQUIRE(in && w && out && wprep, "conv3x3_fwd_tc: null pointer");
+    SIFNN_REQUIRE(Cout <= 64, "conv3x3_fwd_tc: the forward form supports Cout in {16,32,64}");
     SIFNN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "conv3x3_fwd_tc: in_scale/in_shift must both be set or both NULL");
     SIFNN_REQUIRE(sifnn_conv3x3_tc_supported(Cin, Cout, H, W) && B > 0 && B <= 65535, "conv3x3_fwd_tc: unsupported shape Cin=%d Cout=%d H=%d W=%d", Cin, Cout, H, W);
     cudaStream_t st = sifnn::as_stream(stream);

@@ -222,7 +222,7 @@ extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* pa
         const float* isc = aff >= 0 ? w.scale + n.bn_off[aff] : nullptr;
         const float* ish = aff >= 0 ? w.shift + n.bn_off[aff] : nullptr;
         double* st_ptr = (bn && train) ? w.stats + 2 * n.bn_off[i] : nullptr;
-        if (tc_enabled() && sifnn_conv3x3_tc_supported(c.cin, c.cout, hs[l], ws[l])) {
+        if (tc_enabled() && c.cout <= 64 && sifnn_conv3x3_tc_supported(c.cin, c.cout, hs[l], ws[l])) {
             SIFNN_TRY(sifnn_conv3x3_fwd_tc(in, isc, ish, params + n.w_off[i], bn ? nullptr : params + n.bias_off, out, st_ptr, w.wprep, B, c.cin,
                                            c.cout, hs[l], ws[l], stream));
         } else {

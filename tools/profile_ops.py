@@ -43,7 +43,7 @@ def main():
         lib = sifnn_b200.load()
         if a.tc:
             fns = {}
-            if lib.sifnn_conv3x3_tc_supported(ci, co, hw, hw):
+            if co <= 64 and lib.sifnn_conv3x3_tc_supported(ci, co, hw, hw):
                 fns["fwd"] = lambda: ops.conv3x3_fwd(x, w)
                 fns["fwd_tc"] = lambda: ops.conv3x3_fwd_tc(x, w)
                 fns["fwd_aff_tc"] = lambda: ops.conv3x3_fwd_tc(x, w, None, sc, sh)
