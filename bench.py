@@ -154,13 +154,17 @@ def workload_name(mode, batch):
 # --------------------------------------------------------------------------------------------------
 # per-kernel roofline (measured live, CUDA events on the launch stream)
 # --------------------------------------------------------------------------------------------------
-def kernel_rooflines(batch, fp32_peak):
-    """Times every convolution kernel class on the workload's own layer shapes through the per-op C-ABI."""
+def kernel_rooflines(batch, fp32_peak, tensor_peak_eff):
+    """Times every convolution kernel class on the workload's own 18 layer shapes through the per-op C-ABI, using the
+    same kernel choice as the network plan (tcgen05 where the shape is eligible, fp32 SIMT elsewhere)."""
+    import sifnn_b200
     from sifnn_b200 import ops
+    lib = sifnn_b200.load()
     layers = [(2, 16, 256), (16, 16, 256), (16, 16, 128), (16, 16, 128), (16, 32, 128), (32, 32, 64), (32, 32, 64), (32, 64, 64),
               (64, 64, 32), (64, 64, 32), (64, 64, 32), (128, 64, 64), (64, 32, 64), (64, 32, 128), (32, 16, 128), (32, 16, 256),
               (16, 16, 256), (16, 1, 256)]
     dev = "cuda"
+    use_tc = sifnn_b200.tensor_cores_enabled()
 
     def timed(fn, reps=3):
         fn()
@@ -172,24 +176,34 @@ def kernel_rooflines(batch, fp32_peak):
         e1.synchronize()
         return e0.elapsed_time(e1) / reps * 1e-3
 
-    res = {"conv3x3_fwd": [0.0, 0.0, 0], "conv3x3_dgrad": [0.0, 0.0, 0], "conv3x3_wgrad": [0.0, 0.0, 0]}
+    res = {}
+
+    def add(name, t, fl):
+        r = res.setdefault(name, [0.0, 0.0, 0])
+        r[0] += t; r[1] += fl; r[2] += 1
+
     for i, (ci, co, hw) in enumerate(layers):
         x = torch.randn(batch, ci, hw, hw, device=dev)
         dy = torch.randn(batch, co, hw, hw, device=dev)
         w = torch.randn(co, ci, 3, 3, device=dev) * 0.1
         fl = 2.0 * batch * ci * co * 9 * hw * hw
-        t = timed(lambda: ops.conv3x3_fwd(x, w))
-        res["conv3x3_fwd"][0] += t; res["conv3x3_fwd"][1] += fl; res["conv3x3_fwd"][2] += 1
+        if use_tc and co <= 64 and lib.sifnn_conv3x3_tc_supported(ci, co, hw, hw):
+            add("conv3x3_tc_kernel (fwd)", timed(lambda: ops.conv3x3_fwd_tc(x, w)), fl)
+        else:
+            add("conv3x3_kernel (fwd, SIMT)", timed(lambda: ops.conv3x3_fwd(x, w)), fl)
         if i > 0:
-            t = timed(lambda: ops.conv3x3_dgrad(dy, w))
-            res["conv3x3_dgrad"][0] += t; res["conv3x3_dgrad"][1] += fl; res["conv3x3_dgrad"][2] += 1
-        t = timed(lambda: ops.conv3x3_wgrad(x, dy, want_bias=(co == 1)))
-        res["conv3x3_wgrad"][0] += t; res["conv3x3_wgrad"][1] += fl; res["conv3x3_wgrad"][2] += 1
+            if use_tc and lib.sifnn_conv3x3_tc_supported(co, ci, hw, hw):
+                add("conv3x3_tc_kernel (dgrad)", timed(lambda: ops.conv3x3_dgrad_tc(dy, w)), fl)
+            else:
+                add("conv3x3_kernel (dgrad, SIMT)", timed(lambda: ops.conv3x3_dgrad(dy, w)), fl)
+        add("wgrad_kernel (SIMT)", timed(lambda: ops.conv3x3_wgrad(x, dy, want_bias=(co == 1))), fl)
         del x, dy, w
     out = []
     for name, (t, fl, n) in res.items():
-        out.append({"kernel": name, "launches_per_step": n, "ms_per_step": t * 1e3, "achieved": fl / t / 1e12, "unit": "TFLOP/s",
-                    "peak": fp32_peak, "frac": fl / t / 1e12 / fp32_peak})
+        tensor = "tc_kernel" in name
+        peak = tensor_peak_eff if tensor else fp32_peak
+        out.append({"kernel": name, "bound": "tensor" if tensor else "fp32", "launches_per_step": n, "ms_per_step": t * 1e3,
+                    "achieved": fl / t / 1e12, "unit": "TFLOP/s", "peak": peak, "frac": fl / t / 1e12 / peak})
     return out
 
 
@@ -248,8 +262,15 @@ def run_ours(args):
         tr.broadcast_parameters(0)
         unit, per_step, metric = "patches/s", B * n_gpus, f"ModelB {kind.upper()} train patches/s"
 
-        def step(i):
-            return tr.step(*devb[i % nb])
+        use_graph = (not args.no_graph) and world == 1
+        if use_graph:
+            tr.capture(*devb[0])  # whole step as one CUDA graph; inputs are copied into its static buffers each step
+
+            def step(i):
+                return tr.step_graph(*devb[i % nb])
+        else:
+            def step(i):
+                return tr.step(*devb[i % nb])
 
         def step_host(i):
             return tr.step_host(*host[i % nb])
@@ -269,6 +290,8 @@ def run_ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
     launches = lib.sifnn_launch_count() - launches0
+    if mode != "infer" and getattr(tr, "_graph", None) is not None:
+        launches = tr.graph_launches * args.steps  # graph replay: the library's counter only saw the capture
     # end-to-end: pinned host buffers in, result scalars (or the SR image) out, every step
     for i in range(2):
         step_host(i)
@@ -292,19 +315,23 @@ def run_ours(args):
                "data": "synthetic",
                "config": {"workload": workload_name(mode, B), "batch_per_gpu": B, "global_batch": B * n_gpus,
                           "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single", "batchnorm": "local (per-rank statistics)",
-                          "weights": "random init, seed 0", "l2": f"{nb} distinct input batches rotated + {2.7 * B / 32:.1f} GB of activations per step (> 126 MB L2)"},
+                          "weights": "random init, seed 0", "launch": "cuda-graph replay" if (mode != "infer" and n_gpus == 1 and not args.no_graph) else "eager", "l2": f"{nb} distinct input batches rotated + {2.7 * B / 32:.1f} GB of activations per step (> 126 MB L2)"},
                "e2e": {"value": per_step * args.steps / (e2e_ms * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": int(launches), "clocks": clk.summary(),
                "achieved_tflops": flop_per_step * n_gpus * args.steps / (ms * 1e-3) / 1e12}
     if rank == 0 and not args.no_roofline:
         from sifnn_b200 import ops
         fp32_peak = ops.fp32_peak_tflops()
-        per_kernel = kernel_rooflines(B, fp32_peak) if mode != "infer" else kernel_rooflines(B, fp32_peak)[:1]
+        tensor_eff = bf16 / 2.0 / 3.0  # TF32 dense = half the measured bf16 peak; fp32 parity costs 3 TF32 products per MAC
+        per_kernel = kernel_rooflines(B, fp32_peak, tensor_eff)
+        if mode == "infer":
+            per_kernel = [k for k in per_kernel if "fwd" in k["kernel"]]
         top = max(per_kernel, key=lambda r: r["ms_per_step"])
-        out["roofline"] = {"bound": "fp32", "kernel": top["kernel"], "achieved": top["achieved"], "peak": fp32_peak, "unit": "TFLOP/s",
+        out["roofline"] = {"bound": top["bound"], "kernel": top["kernel"], "achieved": top["achieved"], "peak": top["peak"], "unit": "TFLOP/s",
                            "frac": top["frac"], "traffic": None,
-                           "note": "fp32 SIMT kernel: the roof is this GPU's measured FFMA throughput (sifnn_fp32_peak_kernel, best of 5), not in "
-                                   f"MEASURED_PEAKS.json; tensor roof for a 3x-split fp32-accurate MMA would be {bf16:.0f}/3 TFLOP/s ({how})",
+                           "note": "achieved = algorithmic conv FLOPs of the kernel class over the network's 18 layer shapes / CUDA-event time, measured "
+                                   "live through the per-op C-ABI. fp32 peak = this GPU's measured FFMA throughput (sifnn_fp32_peak_kernel, best of 5; not in "
+                                   f"MEASURED_PEAKS.json). tensor peak = {how} bf16 {bf16:.0f} TFLOP/s / 2 (TF32) / 3 (3-term split for fp32 parity) = {tensor_eff:.0f}.",
                            "per_kernel": per_kernel}
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         import sifnn_oracle as O
@@ -349,6 +376,7 @@ def main():
     ap.add_argument("--mode", default="train_sr1", choices=["train_sr1", "train_sr2", "infer"])
     ap.add_argument("--batch", type=int, default=32, help="patches per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=8, help="patches per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the training step eagerly instead of replaying a CUDA graph (single GPU)")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -135,6 +135,16 @@ int sifnn_upcat_bwd(const float* dout, float* dlow, float* dskip,
 int sifnn_bicubic4_cat(const float* lst, const float* ndvi, float* x, int B, int h, int w,
                        sifnn_stream_t stream);
 
+/* Whole-tile driver (reference predict.py:84-103).  lst_tile (Ht,Wt) Kelvin, ndvi_tile (4Ht,4Wt); patch p of the list
+ * is the 64x64 LST window / 256x256 NDVI window at window coordinates (wy[p], wx[p]) (device int arrays).
+ * gather : lst_out (P,1,64,64) = (lst - mean_lst)/std_lst; ndvi_out (P,1,256,256) = (clip(ndvi,-1,1) - mean_ndvi)/std_ndvi
+ * scatter: out_tile[4*64*wy .. , 4*64*wx ..] = sr * std_lst + mean_lst          (predict.py:88-89,96-103) */
+int sifnn_tile_gather(const float* lst_tile, const float* ndvi_tile, const int* wy, const int* wx,
+                      float* lst_out, float* ndvi_out, int P, int Ht, int Wt,
+                      float mean_lst, float std_lst, float mean_ndvi, float std_ndvi, sifnn_stream_t stream);
+int sifnn_tile_scatter(const float* sr, const int* wy, const int* wx, float* out_tile, int P, int Ht, int Wt,
+                       float mean_lst, float std_lst, sifnn_stream_t stream);
+
 /* Fused loss forward + dLoss/dSR.
  * kind 1 = SR1 (train_model_B_predef_filters.py:111-133: Huber(downscale) + Huber(Sobel4)),
  * kind 2 = SR2 (train_model_B_gradFTM.py:99-117: Huber(downscale) + Huber(x - G_0.25(x))).

@@ -14,6 +14,7 @@ from .model import (ModelB_2, DoubleConvolution, UpBlock, ResidualConnection, Do
 from .losses import sr_losses, sr1_losses, sr2_losses, loss_fwd_bwd  # noqa: F401
 from .trainer import Trainer  # noqa: F401
 from .parallel import block_partition, shard_batch, BucketedAllReduce  # noqa: F401
+from .tile import super_resolve_tile, window_list  # noqa: F401
 
 
 

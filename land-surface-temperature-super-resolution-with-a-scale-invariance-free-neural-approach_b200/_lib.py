@@ -83,6 +83,8 @@ SIGNATURES = {
     "sifnn_act_upcat_fwd": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
     "sifnn_upcat_bwd": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
     "sifnn_bicubic4_cat": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
+    "sifnn_tile_gather": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_float] * 4 + [c_void_p]),
+    "sifnn_tile_scatter": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float] * 2 + [c_void_p]),
     "sifnn_loss_fwd_bwd": (c_int, [c_int] + [c_void_p] * 7 + [c_float, c_float] + [c_void_p] * 2 + [c_int] * 3 + [c_void_p]),
     "sifnn_adam_step": (c_int, [c_void_p] * 5 + [c_double] * 4 + [c_float, c_int64, c_void_p]),
     "sifnn_fp32_peak_kernel": (c_int, [c_void_p, c_int, _d, c_void_p]),

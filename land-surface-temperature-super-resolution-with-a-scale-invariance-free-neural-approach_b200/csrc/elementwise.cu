@@ -444,3 +444,71 @@ extern "C" int sifnn_bicubic4_cat(const float* lst, const float* ndvi, float* x,
     bicubic4_cat_kernel<<<grid_for(total, 256), 256, 0, sifnn::as_stream(stream)>>>(lst, ndvi, x, total, h, w);
     return sifnn::check_launch("bicubic4_cat_kernel");
 }
+
+// ==========================================================================================
+// Whole-tile driver kernels (reference predict.py:84-103): gather 64x64 LST windows / 256x256 NDVI windows out of
+// the MODIS tile with the per-window arithmetic fused (NDVI clip to [-1,1], z-score), and scatter the de-normalised
+// super-resolved patches back into the 4x tile.  Patch p of the list covers window (wy[p], wx[p]) (window units).
+// ==========================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256) tile_gather_kernel(const float* __restrict__ lst_tile, const float* __restrict__ ndvi_tile,
+                                                          const int* __restrict__ wy, const int* __restrict__ wx, float* __restrict__ lst_out,
+                                                          float* __restrict__ ndvi_out, int P, int Wt, float mean_lst, float inv_std_lst,
+                                                          float mean_ndvi, float inv_std_ndvi) {
+    // one CTA per (patch, 16-row band of the 256x256 NDVI window); the 64x64 LST window rides along in band 0..3
+    const int p = blockIdx.y, band = blockIdx.x;
+    const int y0 = wy[p] * 64, x0 = wx[p] * 64;
+    const float* nsrc = ndvi_tile + (size_t)(4 * y0 + band * 16) * (4 * Wt) + 4 * x0;
+    float* ndst = ndvi_out + (size_t)p * 65536 + band * 16 * 256;
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+        const int r = i >> 6, c4 = i & 63;
+        float4 v = __ldg(reinterpret_cast<const float4*>(nsrc + (size_t)r * (4 * Wt)) + c4);
+        v.x = (fminf(fmaxf(v.x, -1.f), 1.f) - mean_ndvi) * inv_std_ndvi;
+        v.y = (fminf(fmaxf(v.y, -1.f), 1.f) - mean_ndvi) * inv_std_ndvi;
+        v.z = (fminf(fmaxf(v.z, -1.f), 1.f) - mean_ndvi) * inv_std_ndvi;
+        v.w = (fminf(fmaxf(v.w, -1.f), 1.f) - mean_ndvi) * inv_std_ndvi;
+        reinterpret_cast<float4*>(ndst + r * 256)[c4] = v;
+    }
+    if (band < 4) {
+        const float* lsrc = lst_tile + (size_t)(y0 + band * 16) * Wt + x0;
+        float* ldst = lst_out + (size_t)p * 4096 + band * 16 * 64;
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            const int r = i >> 6, c = i & 63;
+            ldst[r * 64 + c] = (__ldg(lsrc + (size_t)r * Wt + c) - mean_lst) * inv_std_lst;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) tile_scatter_kernel(const float* __restrict__ sr, const int* __restrict__ wy, const int* __restrict__ wx,
+                                                           float* __restrict__ out_tile, int P, int Wt, float mean_lst, float std_lst) {
+    const int p = blockIdx.y, band = blockIdx.x;
+    const int y0 = wy[p] * 256, x0 = wx[p] * 256;
+    const float* src = sr + (size_t)p * 65536 + band * 16 * 256;
+    float* dst = out_tile + (size_t)(y0 + band * 16) * (4 * Wt) + x0;
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+        const int r = i >> 6, c4 = i & 63;
+        float4 v = __ldg(reinterpret_cast<const float4*>(src + r * 256) + c4);
+        v.x = fmaf(v.x, std_lst, mean_lst); v.y = fmaf(v.y, std_lst, mean_lst);
+        v.z = fmaf(v.z, std_lst, mean_lst); v.w = fmaf(v.w, std_lst, mean_lst);
+        reinterpret_cast<float4*>(dst + (size_t)r * (4 * Wt))[c4] = v;
+    }
+}
+
+}  // namespace
+
+extern "C" int sifnn_tile_gather(const float* lst_tile, const float* ndvi_tile, const int* wy, const int* wx, float* lst_out, float* ndvi_out,
+                                 int P, int Ht, int Wt, float mean_lst, float std_lst, float mean_ndvi, float std_ndvi, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(lst_tile && ndvi_tile && wy && wx && lst_out && ndvi_out && P > 0 && P <= 65535, "tile_gather: bad arguments");
+    SIFNN_REQUIRE(Ht >= 64 && Wt >= 64 && Wt % 4 == 0 && std_lst != 0.f && std_ndvi != 0.f, "tile_gather: bad tile shape / statistics");
+    tile_gather_kernel<<<dim3(16, P), 256, 0, sifnn::as_stream(stream)>>>(lst_tile, ndvi_tile, wy, wx, lst_out, ndvi_out, P, Wt, mean_lst, 1.f / std_lst,
+                                                                         mean_ndvi, 1.f / std_ndvi);
+    return sifnn::check_launch("tile_gather_kernel");
+}
+
+extern "C" int sifnn_tile_scatter(const float* sr, const int* wy, const int* wx, float* out_tile, int P, int Ht, int Wt, float mean_lst,
+                                  float std_lst, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(sr && wy && wx && out_tile && P > 0 && P <= 65535 && Ht >= 64 && Wt >= 64, "tile_scatter: bad arguments");
+    tile_scatter_kernel<<<dim3(16, P), 256, 0, sifnn::as_stream(stream)>>>(sr, wy, wx, out_tile, P, Wt, mean_lst, std_lst);
+    return sifnn::check_launch("tile_scatter_kernel");
+}

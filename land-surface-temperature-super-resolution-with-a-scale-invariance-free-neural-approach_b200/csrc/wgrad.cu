@@ -14,6 +14,7 @@
 namespace {
 
 constexpr int WROWS = 16;
+constexpr int WGRAD_STAGES = 2;
 constexpr int IN_STRIDE = 40;
 constexpr int IN_X0 = 3;
 constexpr int IN_COLS = 34;
@@ -204,29 +205,31 @@ __global__ void __launch_bounds__((O_CHUNK / OT) * (K_CHUNK / KT) * 32, 1) wgrad
         y0 = ty * WROWS;
     };
 
+    // NST-deep cp.async ring: the tiles it+1 .. it+NST-1 are in flight while tile `it` is consumed (one tile of
+    // compute is ~2.4 us at full FMA rate, about one DRAM round trip under load, so a single tile of look-ahead
+    // does not cover it).  One commit group per tile, empty groups past the end keep the wait counts uniform.
+    constexpr int NST = WGRAD_STAGES;
+    auto issue = [&](int tile, int slot) {
+        if (tile < a.total_tiles) {
+            int b, x0, y0;
+            tile_origin(tile, b, x0, y0);
+            float* nin = smem + slot * STAGE;
+            wgrad_issue_fill<O_CHUNK, K_CHUNK, NT>(nin, nin + K_CHUNK * IN_PLANE, a, b, x0, y0, k0, o0, a.vec_ok && x0 + 32 <= a.W, tid);
+        }
+        sifnn::cp_async_commit();
+    };
     int it = 0;
-    if (s < a.total_tiles) {
-        int b, x0, y0;
-        tile_origin(s, b, x0, y0);
-        wgrad_issue_fill<O_CHUNK, K_CHUNK, NT>(smem, smem + K_CHUNK * IN_PLANE, a, b, x0, y0, k0, o0, a.vec_ok && x0 + 32 <= a.W, tid);
-    }
-    sifnn::cp_async_commit();
+#pragma unroll
+    for (int p = 0; p < NST - 1; ++p) issue(s + p * S, p);
     for (int tile = s; tile < a.total_tiles; tile += S, ++it) {
-        float* in_s = smem + (it & 1) * STAGE;
+        const int slot = it % NST;
+        float* in_s = smem + slot * STAGE;
         float* dy_s = in_s + K_CHUNK * IN_PLANE;
         int b, x0, y0;
         tile_origin(tile, b, x0, y0);
         const bool vec_ok = a.vec_ok && x0 + 32 <= a.W;
-        if (tile + S < a.total_tiles) {
-            int nb, nx0, ny0;
-            tile_origin(tile + S, nb, nx0, ny0);
-            float* nin = smem + ((it + 1) & 1) * STAGE;
-            wgrad_issue_fill<O_CHUNK, K_CHUNK, NT>(nin, nin + K_CHUNK * IN_PLANE, a, nb, nx0, ny0, k0, o0, a.vec_ok && nx0 + 32 <= a.W, tid);
-            sifnn::cp_async_commit();
-            sifnn::cp_async_wait<1>();
-        } else {
-            sifnn::cp_async_wait<0>();
-        }
+        issue(tile + (NST - 1) * S, (it + NST - 1) % NST);   // refills the slot consumed in the previous iteration
+        sifnn::cp_async_wait<NST - 1>();
         if (AFFINE) {
             if (it == 0) __syncthreads();  // sc_s / sh_s
             wgrad_affine_pass<K_CHUNK, NT>(in_s, sc_s, sh_s, K, k0, vec_ok, tid);
@@ -370,7 +373,7 @@ Plan make_plan(int B, int K, int O, int H, int W) {
 template <int OT, int KT, int O_CHUNK, int K_CHUNK, bool BIAS>
 int launch_wgrad(const WgradArgs& a, const Plan& p, bool affine, cudaStream_t st) {
     constexpr int NT = (O_CHUNK / OT) * (K_CHUNK / KT) * 32;
-    constexpr size_t smem = 2 * (size_t)(K_CHUNK * (WROWS + 2) * IN_STRIDE + O_CHUNK * WROWS * 32) * sizeof(float);  // two stages
+    constexpr size_t smem = WGRAD_STAGES * (size_t)(K_CHUNK * (WROWS + 2) * IN_STRIDE + O_CHUNK * WROWS * 32) * sizeof(float);
     auto k_aff = wgrad_kernel<OT, KT, O_CHUNK, K_CHUNK, true, BIAS>;
     auto k_pln = wgrad_kernel<OT, KT, O_CHUNK, K_CHUNK, false, BIAS>;
     static bool attr_done = false;

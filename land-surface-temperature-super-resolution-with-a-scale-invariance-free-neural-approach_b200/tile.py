@@ -1,0 +1,57 @@
+"""Whole-tile inference (reference predict.py:81-105): a MODIS tile (LST 1200x1200 K, NDVI 4800x4800) is cut into
+64x64 / 256x256 windows, every window goes through ModelB and the de-normalised result is written into the 4x tile.
+
+The reference runs one batch-1 forward per window in a Python double loop; here the window list is gathered on the
+device in batches (clip + z-score fused into the gather kernel), pushed through the fused bicubic front-end and the
+network, and scattered back (de-normalisation fused).  Windows that are not full 64x64 are skipped and stay 0 --
+like the reference (predict.py:95), which leaves the trailing 48-pixel strip of a 1200-pixel tile untouched.
+Across ranks the window list is block-partitioned (no collective); each rank fills its own part of the output."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import SifnnError
+from .model import ModelB_2, _stream
+from .parallel import block_partition
+
+
+def window_list(ht: int, wt: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Window coordinates in the reference's loop order (predict.py:84-85), full 64x64 windows only."""
+    ny, nx = ht // 64, wt // 64
+    wy = torch.arange(ny, dtype=torch.int32).repeat_interleave(nx)
+    wx = torch.arange(nx, dtype=torch.int32).repeat(ny)
+    return wy, wx
+
+
+@torch.inference_mode()
+def super_resolve_tile(model: ModelB_2, lst_tile: torch.Tensor, ndvi_tile: torch.Tensor, stats: Dict[str, float], batch: int = 64,
+                       rank: int = 0, world_size: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LST_SR tile (4Ht, 4Wt) in Kelvin.  ``stats`` has mean_lst/std_lst/mean_ndvi/std_ndvi like data/statistics.json.
+    With world_size > 1 only this rank's block of windows is computed (the rest of ``out`` is left as passed in)."""
+    if not (lst_tile.is_cuda and ndvi_tile.is_cuda) or lst_tile.dtype != torch.float32 or ndvi_tile.dtype != torch.float32:
+        raise SifnnError("super_resolve_tile needs fp32 CUDA tensors")
+    ht, wt = lst_tile.shape
+    if tuple(ndvi_tile.shape) != (4 * ht, 4 * wt) or wt % 4:
+        raise SifnnError(f"expected NDVI (4Ht,4Wt) for LST {(ht, wt)}, got {tuple(ndvi_tile.shape)}")
+    if model.training:
+        raise SifnnError("super_resolve_tile needs model.eval()")
+    lst_tile, ndvi_tile = lst_tile.contiguous(), ndvi_tile.contiguous()
+    dev = lst_tile.device
+    if out is None:
+        out = torch.zeros((4 * ht, 4 * wt), dtype=torch.float32, device=dev)
+    wy, wx = window_list(ht, wt)
+    start, cnt = block_partition(wy.numel(), world_size)[rank]
+    wy, wx = wy[start:start + cnt].to(dev), wx[start:start + cnt].to(dev)
+    ml, sl, mn, sn = (float(stats[k]) for k in ("mean_lst", "std_lst", "mean_ndvi", "std_ndvi"))
+    for i in range(0, cnt, batch):
+        p = min(batch, cnt - i)
+        lst = torch.empty((p, 1, 64, 64), dtype=torch.float32, device=dev)
+        ndvi = torch.empty((p, 1, 256, 256), dtype=torch.float32, device=dev)
+        _lib.call("sifnn_tile_gather", lst_tile.data_ptr(), ndvi_tile.data_ptr(), wy[i:].data_ptr(), wx[i:].data_ptr(), lst.data_ptr(),
+                  ndvi.data_ptr(), p, ht, wt, ml, sl, mn, sn, _stream())
+        sr = model.forward_from_lowres(lst, ndvi)
+        _lib.call("sifnn_tile_scatter", sr.data_ptr(), wy[i:].data_ptr(), wx[i:].data_ptr(), out.data_ptr(), p, ht, wt, ml, sl, _stream())
+    return out

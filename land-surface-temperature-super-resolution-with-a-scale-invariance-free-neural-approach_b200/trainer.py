@@ -99,9 +99,12 @@ class Trainer:
     def step_host(self, lst_pinned: torch.Tensor, ndvi_pinned: torch.Tensor) -> Tuple[float, float, float]:
         """End-to-end step from (pinned) HOST buffers: H2D copies, step, D2H of the three scalars."""
         dev = next(self.model.parameters()).device
-        lst = lst_pinned.to(dev, non_blocking=True)
-        ndvi = ndvi_pinned.to(dev, non_blocking=True)
-        losses = self.step(lst, ndvi)
+        if self._graph is not None and tuple(lst_pinned.shape) == tuple(self._static_lst.shape):
+            losses = self.step_graph(lst_pinned, ndvi_pinned)      # H2D straight into the graph's static buffers
+        else:
+            lst = lst_pinned.to(dev, non_blocking=True)
+            ndvi = ndvi_pinned.to(dev, non_blocking=True)
+            losses = self.step(lst, ndvi)
         ds, pl, loss = losses.cpu().tolist()
         return ds, pl, loss
 
@@ -134,8 +137,10 @@ class Trainer:
                 self._step_impl(self._static_lst, self._static_ndvi, None)
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
+        n0 = _lib.load().sifnn_launch_count()
         with torch.cuda.graph(g):
             self._static_losses, _ = self._step_impl(self._static_lst, self._static_ndvi, None)
+        self.graph_launches = int(_lib.load().sifnn_launch_count() - n0)  # kernels of this library inside one replay
         self._graph = g
 
     def step_graph(self, lst: torch.Tensor, ndvi: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,56 @@
+"""Whole-tile driver (-m gpu): gather -> fused bicubic front-end -> ModelB -> scatter against the reference's
+per-window loop (predict.py:84-103) restated with the oracle; block-partitioned sharding reproduces the full tile."""
+import numpy as np
+import pytest
+import torch
+
+import model as model_mod
+import sifnn_b200
+import sifnn_oracle as O
+from conftest import load_ckpt, rel_err
+
+pytestmark = pytest.mark.gpu
+STATS = dict(mean_lst=O.MEAN_LST, std_lst=O.STD_LST, mean_ndvi=O.MEAN_NDVI, std_ndvi=O.STD_NDVI)
+
+
+def make_tile(ht=176, wt=200, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    lst = 300 + 8 * torch.rand(ht, wt, generator=g)
+    ndvi = 0.6 + 0.6 * torch.randn(4 * ht, 4 * wt, generator=g)  # some values outside [-1, 1]: exercises the clip
+    return lst, ndvi
+
+
+def oracle_tile(sd, lst, ndvi):
+    """predict.py:81-103 with the oracle forward: windows of 64, incomplete windows skipped, output starts at 0."""
+    out = torch.zeros(ndvi.shape)
+    for i in range(0, lst.shape[0], 64):
+        for j in range(0, lst.shape[1], 64):
+            lb = lst[i:i + 64, j:j + 64]
+            if lb.shape != (64, 64):
+                continue
+            nb = ndvi[4 * i:4 * (i + 64), 4 * j:4 * (j + 64)].clamp(-1, 1)
+            l = ((lb - O.MEAN_LST) / O.STD_LST)[None, None]
+            n = ((nb - O.MEAN_NDVI) / O.STD_NDVI)[None, None]
+            with torch.no_grad():
+                sr = O.forward(sd, torch.cat((O.bicubic_up4(l), n), 1))[0, 0]
+            out[4 * i:4 * (i + 64), 4 * j:4 * (j + 64)] = sr * O.STD_LST + O.MEAN_LST
+    return out
+
+
+def test_tile_matches_reference_loop_and_shards():
+    sd = load_ckpt("1009")
+    m = model_mod.ModelB_2(2)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    lst, ndvi = make_tile()
+    ref = oracle_tile(sd, lst, ndvi)
+    out = sifnn_b200.super_resolve_tile(m, lst.cuda(), ndvi.cuda(), STATS, batch=4)
+    assert out.shape == ref.shape
+    assert float((out.cpu() - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+    assert float(out[:, 4 * 192:].abs().max()) == 0.0 and float(out[4 * 128:].abs().max()) == 0.0  # incomplete windows stay 0
+    # 3-way block partition of the 2x3 = 6 windows, every rank writing into the same buffer == the full tile
+    acc = torch.zeros_like(out)
+    for r in range(3):
+        sifnn_b200.super_resolve_tile(m, lst.cuda(), ndvi.cuda(), STATS, batch=8, rank=r, world_size=3, out=acc)
+    assert torch.equal(acc, out)
+    assert sifnn_b200.window_list(1200, 1200)[0].numel() == 324
