@@ -298,21 +298,27 @@ class ModelB_2(nn.Module):
             raise SifnnError(f"expected (B,{self.in_channels},H,W) with H, W multiples of 8; got {tuple(x.shape)}")
         return x.contiguous()
 
-    def _run_forward(self, x: torch.Tensor, train: bool, keep: bool):
+    def _workspace_bytes(self, B: int, H: int, W: int, keep: bool) -> int:
+        st = self._native_state()
+        nbytes = _lib.load().sifnn_modelb_workspace_bytes(ctypes.byref(st["cfg"]), B, H, W, 1 if keep else 0)
+        if nbytes == 0:
+            raise SifnnError(f"unsupported shape (B={B}, H={H}, W={W})")
+        return nbytes
+
+    def _run_forward(self, x: torch.Tensor, train: bool, keep: bool, ws: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None):
         st = self._ensure_flat(x.device)
-        lib = _lib.load()
         B, _, H, W = x.shape
         key = (B, H, W, bool(keep), x.device)
-        nbytes = lib.sifnn_modelb_workspace_bytes(ctypes.byref(st["cfg"]), B, H, W, 1 if keep else 0)
-        if nbytes == 0:
-            raise SifnnError(f"unsupported shape {tuple(x.shape)}")
-        ws = self._ws.take(key, nbytes, x.device)
-        y = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+        own_ws = ws is None
+        if own_ws:
+            ws = self._ws.take(key, self._workspace_bytes(B, H, W, keep), x.device)
+        if y is None:
+            y = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
         _lib.call("sifnn_modelb_forward", ctypes.byref(st["cfg"]), st["flat"].data_ptr(), st["rm"].data_ptr(), st["rv"].data_ptr(),
                   x.data_ptr(), y.data_ptr(), ws.data_ptr(), B, H, W, 1 if train else 0, _stream())
         if train:
             torch._foreach_add_(st["counters"], 1)
-        if keep:
+        if keep or not own_ws:
             return y, ws, key
         self._ws.give(key, ws)
         return y, None, key
@@ -348,7 +354,7 @@ class ModelB_2(nn.Module):
         return self.forward(bicubic4_cat(lst, ndvi))
 
 
-def bicubic4_cat(lst: torch.Tensor, ndvi: torch.Tensor) -> torch.Tensor:
+def bicubic4_cat(lst: torch.Tensor, ndvi: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x = cat(bicubic_x4(lst), ndvi) on the device (reference utils.py:180 + train_model_B_gradFTM.py:94)."""
     if not (lst.is_cuda and ndvi.is_cuda) or lst.dtype != torch.float32 or ndvi.dtype != torch.float32:
         raise SifnnError("bicubic4_cat needs fp32 CUDA tensors")
@@ -356,6 +362,6 @@ def bicubic4_cat(lst: torch.Tensor, ndvi: torch.Tensor) -> torch.Tensor:
     if c != 1 or tuple(ndvi.shape) != (B, 1, 4 * h, 4 * w):
         raise SifnnError(f"bicubic4_cat: expected lst (B,1,h,w) and ndvi (B,1,4h,4w); got {tuple(lst.shape)} / {tuple(ndvi.shape)}")
     lst, ndvi = lst.contiguous(), ndvi.contiguous()
-    x = torch.empty((B, 2, 4 * h, 4 * w), dtype=torch.float32, device=lst.device)
+    x = out if out is not None else torch.empty((B, 2, 4 * h, 4 * w), dtype=torch.float32, device=lst.device)
     _lib.call("sifnn_bicubic4_cat", lst.data_ptr(), ndvi.data_ptr(), x.data_ptr(), B, h, w, _stream())
     return x

@@ -122,31 +122,83 @@ class Trainer:
             m.train(was)
         return losses
 
-    # ------------------------------------------------------------------ CUDA graph replay (single GPU)
+    # ------------------------------------------------------------------ CUDA graph replay
     def capture(self, lst: torch.Tensor, ndvi: torch.Tensor) -> None:
-        """Capture the whole step into a CUDA graph for shapes like (lst, ndvi); afterwards
-        ``step_graph`` copies new data into the static buffers and replays it."""
-        if self.world > 1:
-            raise SifnnError("graph capture is single-GPU; the data-parallel step runs eagerly around the NCCL calls")
-        self._static_lst, self._static_ndvi = lst.clone(), ndvi.clone()
-        self._opt_state(lst.device)
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(2):  # warm-up: allocations, lazy attribute setup
-                self._step_impl(self._static_lst, self._static_ndvi, None)
-        torch.cuda.current_stream().wait_stream(s)
-        g = torch.cuda.CUDAGraph()
-        n0 = _lib.load().sifnn_launch_count()
-        with torch.cuda.graph(g):
-            self._static_losses, _ = self._step_impl(self._static_lst, self._static_ndvi, None)
-        self.graph_launches = int(_lib.load().sifnn_launch_count() - n0)  # kernels of this library inside one replay
-        self._graph = g
+        """Capture the step for inputs shaped like (lst, ndvi); afterwards ``step_graph`` copies new data into the
+        static buffers and replays.  Single GPU: one graph for the whole step.  Data parallel: three graphs --
+        [input stage, forward, loss, decoder backward] | [encoder backward] | [Adam] -- with the two NCCL bucket
+        all-reduces issued eagerly between them, so the decoder bucket still overlaps the encoder backward."""
+        m = self.model
+        if not m.training:
+            raise SifnnError("Trainer.capture needs model.train()")
+        dev = lst.device
+        st, opt = self._opt_state(dev)
+        B, _, h, w = lst.shape
+        H, W = 4 * h, 4 * w
+        sb = self._static = {
+            "lst": lst.clone(), "ndvi": ndvi.clone(),
+            "x": torch.empty((B, 2, H, W), dtype=torch.float32, device=dev),
+            "y": torch.empty((B, 1, H, W), dtype=torch.float32, device=dev),
+            "dsr": torch.empty((B, 1, H, W), dtype=torch.float32, device=dev),
+            "losses": torch.zeros(3, dtype=torch.float64, device=dev),
+            "ws": torch.empty(m._workspace_bytes(B, H, W, True), dtype=torch.uint8, device=dev),
+        }
+        self._static_lst, self._static_ndvi, self._static_losses = sb["lst"], sb["ndvi"], sb["losses"]
+        fgrad, dec = st["fgrad"], st["dec_off"]
+        lib = _lib.load()
+
+        def seg_front():
+            bicubic4_cat(sb["lst"], sb["ndvi"], out=sb["x"])
+            m._run_forward(sb["x"], train=True, keep=True, ws=sb["ws"], y=sb["y"])
+            loss_fwd_bwd(self.kind, sb["y"], sb["lst"], sb["ndvi"], self.alpha, self.gamma, want_grad=True, losses=sb["losses"], dsr=sb["dsr"])
+            m._run_backward(sb["x"], sb["dsr"], sb["ws"], phase=0 if self.world == 1 else 1)
+
+        def seg_encoder():
+            m._run_backward(sb["x"], sb["dsr"], sb["ws"], phase=2)
+
+        def seg_adam():
+            _lib.call("sifnn_adam_step", st["flat"].data_ptr(), fgrad.data_ptr(), opt["m"].data_ptr(), opt["v"].data_ptr(),
+                      opt["t"].data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world, st["n"], _stream())
+
+        segs = [seg_front, seg_adam] if self.world == 1 else [seg_front, seg_encoder, seg_adam]
+        # warm-up outside capture (lazy attribute setup, cudaFuncSetAttribute, allocator) -- two eager steps
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._replay_or_run(segs, eager=True, fgrad=fgrad, dec=dec)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = lib.sifnn_launch_count()
+        graphs = []
+        for fn in segs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            graphs.append(g)
+        self.graph_launches = int(lib.sifnn_launch_count() - n0)  # kernels of this library inside one replayed step
+        self._graph = graphs
+        self._segs = segs
+        self._ar = (fgrad, dec)
+
+    def _replay_or_run(self, segs, eager: bool, fgrad, dec):
+        run = (lambda i: segs[i]()) if eager else (lambda i: self._graph[i].replay())
+        if self.world == 1:
+            run(0)
+            run(1)
+            return
+        ar = BucketedAllReduce(fgrad, dec)
+        run(0)
+        ar.start(0)      # decoder bucket overlaps the encoder backward
+        run(1)
+        ar.start(1)
+        ar.finish()
+        run(2)
 
     def step_graph(self, lst: torch.Tensor, ndvi: torch.Tensor) -> torch.Tensor:
         if self._graph is None:
             raise SifnnError("call capture() first")
         self._static_lst.copy_(lst, non_blocking=True)
         self._static_ndvi.copy_(ndvi, non_blocking=True)
-        self._graph.replay()
+        self._replay_or_run(self._segs, eager=False, fgrad=self._ar[0], dec=self._ar[1])
         return self._static_losses

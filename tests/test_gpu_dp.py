@@ -45,6 +45,24 @@ def _worker(rank, world, port, out):
         sl = lambda t: sifnn_b200.shard_batch(t, rank, world).cuda()
         losses = tr.step(sl(lst), sl(ndvi)).cpu().numpy()
         out[rank] = (torch.cat([p.detach().reshape(-1) for p in m.parameters()]).cpu().numpy(), losses)
+        # the same step replayed from CUDA graphs (three segments around the two NCCL buckets) must reproduce eager
+        ma, mb = (model_mod.ModelB_2(in_channels=2) for _ in range(2))
+        for mm in (ma, mb):
+            mm.load_state_dict(sd)
+            mm.cuda().train()
+        ta, tb = sifnn_b200.Trainer(ma, "sr2", 0.5, -0.25, 1e-3), sifnn_b200.Trainer(mb, "sr2", 0.5, -0.25, 1e-3)
+        sd0 = {k: v.clone() for k, v in mb.state_dict().items()}
+        tb.capture(sl(lst), sl(ndvi))
+        mb.load_state_dict(sd0)
+        for k in ("m", "v", "t"):
+            tb._opt[k].zero_()
+        for _ in range(2):
+            la = ta.step(sl(lst), sl(ndvi))
+            lb = tb.step_graph(sl(lst), sl(ndvi)).clone()
+        pa = torch.cat([p.detach().reshape(-1) for p in ma.parameters()])
+        pb = torch.cat([p.detach().reshape(-1) for p in mb.parameters()])
+        assert torch.allclose(la, lb, rtol=1e-6), (la, lb)
+        assert float((pa - pb).abs().max()) <= 1e-6 * float(pa.abs().max()), float((pa - pb).abs().max())
     finally:
         dist.destroy_process_group()
 
