@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             int b, y0, x0;
             tile_coords(tile, b, y0, x0);
-            const int jlo = (x0 == 0) ? 4 : 3, jhi = (x0 + MM >= W) ? MM + 3 : MM + 4;  // staged columns that exist in the image
+            const int jlo = (x0 == 0) ? 4 : 3, jhi = min(MM + 4, W - x0 + 3);  // staged columns that exist in the image (tiles may stick out)
             for (int ch = 0; ch < nchunks; ++ch, ++g) {
                 const int s = g % S, rs = g % RS;
                 float* a_hi = stage0 + (size_t)s * SM::STAGE;
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
                     tmem_ld8(taddr, d1);
                     tmem_ld8(taddr + N, d2);
                     tmem_ld_wait();
-                    if (y < H && lane_ok) {
+                    if (y < H && lane_ok && x < W) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float v = d1[j] + d2[j];
@@ -439,7 +439,7 @@ int launch_tc(const TcArgs& a0, cudaStream_t st) {
         attr_done = true;
     }
     TcArgs a = a0;
-    a.tiles_x = a.W / MM;
+    a.tiles_x = (a.W + MM - 1) / MM;
     a.tiles_y = (a.H + R - 1) / R;
     a.num_tiles = a.B * a.tiles_x * a.tiles_y;
     // activation tensor as a 3-D TMA tensor {W, H, B*K planes}; box = {136 columns, R+2 rows, 8 planes}
@@ -481,8 +481,10 @@ int dispatch_tc(const TcArgs& a, cudaStream_t st) {
 }  // namespace
 
 extern "C" int sifnn_conv3x3_tc_supported(int Cin, int Cout, int H, int W) {
-    // 128 output channels (the data gradient of ub1's first convolution) only in the 64-pixel-wide form: the stage would not fit otherwise
-    return (W % 64 == 0) && (Cin % 8 == 0) && Cin <= 128 && (Cout == 16 || Cout == 32 || Cout == 64 || (Cout == 128 && W % 128 != 0)) && H >= 1;
+    // Any width that is a multiple of 4 (TMA row pitch) and at least 16: multiples of 128 use M = 128 MMAs, everything else M = 64 MMAs
+    // with the columns past the image masked.  128 output channels (data gradient of ub1's first convolution) only in the M = 64
+    // form: the stage would not fit otherwise.
+    return (W % 4 == 0) && W >= 16 && (Cin % 8 == 0) && Cin <= 128 && (Cout == 16 || Cout == 32 || Cout == 64 || (Cout == 128 && W % 128 != 0)) && H >= 1;
 }
 
 extern "C" size_t sifnn_conv3x3_tc_wprep_bytes(int Cin, int Cout) { return (size_t)(Cin / 8) * 9 * 2 * 2 * Cout * 4 * sizeof(float); }

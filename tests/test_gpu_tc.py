@@ -21,7 +21,8 @@ def ref_conv(x, w, b=None):
 
 
 SHAPES = [(2, 16, 16, 8, 128), (1, 32, 16, 6, 256), (2, 64, 32, 5, 128), (1, 8, 64, 4, 128), (3, 16, 32, 16, 128), (1, 128, 64, 3, 128),
-          (2, 32, 32, 64, 64), (1, 128, 64, 10, 64), (3, 64, 32, 7, 64), (2, 16, 16, 9, 64), (40, 32, 64, 64, 64)]
+          (2, 32, 32, 64, 64), (1, 128, 64, 10, 64), (3, 64, 32, 7, 64), (2, 16, 16, 9, 64), (40, 32, 64, 64, 64),
+          (4, 64, 64, 32, 32), (2, 16, 32, 5, 96), (3, 32, 16, 8, 16), (2, 8, 16, 6, 20)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -32,7 +33,7 @@ def test_tc_fwd_plain(shape):
     assert rel_err(y, ref_conv(x, w)) < TOL
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 16, 8, 128), (1, 32, 64, 6, 256), (2, 32, 32, 64, 64), (2, 64, 64, 6, 64)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 8, 128), (1, 32, 64, 6, 256), (2, 32, 32, 64, 64), (2, 64, 64, 6, 64), (3, 64, 64, 32, 32)])
 def test_tc_fwd_affine_stats_bias(shape):
     B, Cin, Cout, H, W = shape
     x, w = rnd(B, Cin, H, W, seed=4), rnd(Cout, Cin, 3, 3, seed=5, scale=0.2)
@@ -47,7 +48,8 @@ def test_tc_fwd_affine_stats_bias(shape):
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 16, 8, 128), (1, 16, 32, 6, 256), (2, 64, 32, 5, 128), (1, 32, 64, 4, 128),
-                                   (2, 128, 64, 64, 64), (2, 32, 32, 9, 64), (1, 128, 64, 5, 64), (2, 64, 32, 64, 64)])
+                                   (2, 128, 64, 64, 64), (2, 32, 32, 9, 64), (1, 128, 64, 5, 64), (2, 64, 32, 64, 64),
+                                   (4, 64, 64, 32, 32), (2, 32, 16, 7, 96), (2, 16, 16, 8, 16)])
 def test_tc_dgrad(shape):
     B, Cin, Cout, H, W = shape
     w, dy = rnd(Cout, Cin, 3, 3, seed=8, scale=0.2), rnd(B, Cout, H, W, seed=9)
