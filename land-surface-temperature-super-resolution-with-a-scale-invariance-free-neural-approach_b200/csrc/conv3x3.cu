@@ -425,7 +425,10 @@ constexpr int BORDER_OC = 16;  // output-channel chunk staged in shared memory
 constexpr int BORDER_KC = 32;  // input channels per CTA (4 warps x 8)
 
 __global__ void __launch_bounds__(128) dgrad_border_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
-                                                           int Cin, int Cout, int H, int W, int cols_pass) {
+                                                           int Cin, int Cout, int H, int W, int mode) {
+    // mode 0: rows pass incl. the corner cross terms; 1: columns pass; 2: columns pass incl. the corner cross terms (used when
+    // the row terms were already folded into the main kernel as extra tap MMAs, see conv3x3_tc.cu)
+    const int cols_pass = mode != 0;
     __shared__ __align__(16) float ws[BORDER_OC * 5 * BORDER_KC];  // [o][slot: 3 main taps + 2 corner taps][k]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
@@ -445,11 +448,15 @@ __global__ void __launch_bounds__(128) dgrad_border_kernel(const float* __restri
         p = i; q = side ? W - 1 : 0;
         t0 = side ? 2 : 0; tstep = 3; r0 = p + 1; dr = -1; c0 = q; dc = 0;
     }
-    // corner cross term (rows pass only): slot 3 = tap (ky_e, 0), slot 4 = tap (ky_e, 2), on dy at the pixel itself
+    // corner cross term, on dy at the pixel itself.  Rows pass: slot 3 = tap (ky_e, 0), slot 4 = tap (ky_e, 2);
+    // columns pass (mode 2): slot 3 = tap (0, kx_e), slot 4 = tap (2, kx_e).
     int cslot = -1;
-    if (!cols_pass && active) {
+    if (mode == 0 && active) {
         if (q == 0) cslot = 3;
         else if (q == W - 1) cslot = 4;
+    } else if (mode == 2 && active) {
+        if (p == 0) cslot = 3;
+        else if (p == H - 1) cslot = 4;
     }
     const size_t plane = (size_t)H * W;
     const float* dyb = dy + (size_t)b * Cout * plane;
@@ -484,7 +491,8 @@ __global__ void __launch_bounds__(128) dgrad_border_kernel(const float* __restri
             const int o = idx / (5 * BORDER_KC);
             int t;
             if (slot < 3) t = t0 + slot * tstep;
-            else t = (slot == 3) ? (side ? 6 : 0) : (side ? 8 : 2);
+            else if (!cols_pass) t = (slot == 3) ? (side ? 6 : 0) : (side ? 8 : 2);
+            else t = (slot == 3) ? (side ? 2 : 0) : (side ? 8 : 6);
             ws[idx] = (kc0 + k < Cin) ? __ldg(w + ((size_t)(ob + o) * Cin + kc0 + k) * 9 + t) : 0.f;
         }
         __syncthreads();
@@ -576,21 +584,25 @@ extern "C" int sifnn_conv3x3_dgrad(const float* dy, const float* w, float* dx, i
     return sifnn_conv3x3_dgrad_border(dy, w, dx, B, Cin, Cout, H, W, stream);
 }
 
+static int launch_border(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H, int W, int mode, cudaStream_t st) {
+    const int L = mode ? H : W;
+    dim3 grid(2 * ((L + 31) / 32), B, (Cin + BORDER_KC - 1) / BORDER_KC);
+    dgrad_border_kernel<<<grid, 128, 0, st>>>(dy, w, dx, Cin, Cout, H, W, mode);
+    return sifnn::check_launch("dgrad_border_kernel");
+}
+
 extern "C" int sifnn_conv3x3_dgrad_border(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H, int W,
                                           sifnn_stream_t stream) {
     SIFNN_REQUIRE(dy && w && dx && B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && H >= 2 && W >= 2, "conv3x3_dgrad_border: bad arguments");
     cudaStream_t st = sifnn::as_stream(stream);
-    for (int cols_pass = 0; cols_pass < 2; ++cols_pass) {
-        const int L = cols_pass ? H : W;
-        dim3 grid(2 * ((L + 31) / 32), B, (Cin + BORDER_KC - 1) / BORDER_KC);
-        dgrad_border_kernel<<<grid, 128, 0, st>>>(dy, w, dx, Cin, Cout, H, W, cols_pass);
-        if (cols_pass == 0) SIFNN_TRY(sifnn::check_launch("dgrad_border_kernel"));
-    }
-    return sifnn::check_launch("dgrad_border_kernel");
+    SIFNN_TRY(launch_border(dy, w, dx, B, Cin, Cout, H, W, 0, st));
+    return launch_border(dy, w, dx, B, Cin, Cout, H, W, 1, st);
 }
 
 extern "C" int sifnn_conv3x3_dgrad_tc(const float* dy, const float* w, float* dx, int accumulate, void* wprep, int B, int Cin, int Cout,
                                       int H, int W, sifnn_stream_t stream) {
+    // the tensor-core kernel folds the top/bottom row terms in as extra tap MMAs; only the column terms (+ corners) are left
     SIFNN_TRY(sifnn_conv3x3_dgrad_tc_main(dy, w, dx, accumulate, wprep, B, Cin, Cout, H, W, stream));
-    return sifnn_conv3x3_dgrad_border(dy, w, dx, B, Cin, Cout, H, W, stream);
+    SIFNN_REQUIRE(H >= 2 && W >= 2, "conv3x3_dgrad_tc: bad shape");
+    return launch_border(dy, w, dx, B, Cin, Cout, H, W, 2, sifnn::as_stream(stream));
 }

@@ -239,6 +239,8 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
         constexpr uint32_t idesc2 = make_idesc(MM, N);      // a_lo x  w_hi
         int g = 0, it = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+            int b, y0, x0;
+            tile_coords(tile, b, y0, x0);
             const int ab = it & 1;
             if (it >= 2) mbar_wait(acc_empty + ab, ((it >> 1) - 1) & 1);
             tc_fence_after();
@@ -269,6 +271,23 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
                             // columns [0,N) receive only a_hi*w_hi; both small cross terms go to columns [N,2N).
                             umma_tf32(d, da_hi + oa, db + ob, idesc1, t == 0 ? first : 1u);
                             umma_tf32(d + N, da_lo + oa, db + ob, idesc2, 1u);
+                        }
+                        if (PAD == 1) {
+                            // Data-gradient form: adjoint of the forward's replicate padding along y.  The forward read image row 0
+                            // (H-1) once more through the clamped index, so the first (last) image row receives its own dy row a
+                            // second time through the ky = 0 (ky = 2) weights -- three extra tap MMAs on the tile row of the output
+                            // row itself.  (The column terms and the four corners are added by dgrad_border_kernel, mode 2.)
+                            const int y = y0 + r;
+                            if (y == 0 || y == H - 1) {
+                                const int tb = (y == 0) ? 6 : 0;  // flipped taps: (ty = 2, tx) carries w[ky = 0][2 - tx]; (ty = 0, tx) carries w[ky = 2][..]
+#pragma unroll
+                                for (int tx = 0; tx < 3; ++tx) {
+                                    const uint64_t oa = (uint64_t)((r + 1) * TC_PITCH + tx);
+                                    const uint64_t ob = (uint64_t)((tb + tx) * 2 * 2 * N);
+                                    umma_tf32(d, da_hi + oa, db + ob, idesc1, 1u);
+                                    umma_tf32(d + N, da_lo + oa, db + ob, idesc2, 1u);
+                                }
+                            }
                         }
                     }
                     umma_commit(ab_empty + s);                        // stage reusable once these MMAs have read it
