@@ -82,6 +82,15 @@ int sifnn_conv3x3_wgrad(const float* in, const float* in_scale, const float* in_
                         const float* dy, float* dw, float* dbias, void* workspace,
                         int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
 
+/* Same weight gradient on the tcgen05 tensor cores (pixels = MMA K dimension, MN-major operands, 3-term TF32 split;
+ * csrc/wgrad_tc.cu).  Shapes: Cin == 16 or a multiple of 32, Cout in {16,32,64}, W a multiple of 16
+ * (sifnn_conv3x3_wgrad_tc_supported); no dbias.  workspace: sifnn_conv3x3_wgrad_tc_workspace() bytes. */
+int sifnn_conv3x3_wgrad_tc_supported(int Cin, int Cout, int H, int W);
+size_t sifnn_conv3x3_wgrad_tc_workspace(int B, int Cin, int Cout, int H, int W);
+int sifnn_conv3x3_wgrad_tc(const float* in, const float* in_scale, const float* in_shift,
+                           const float* dy, float* dw, void* workspace,
+                           int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+
 /* nn.BatchNorm2d training statistics -> affine (model.py:136,139,508).
  * stats (2*C doubles: sum, sumsq over n = B*H*W).  Writes scale = gamma*invstd,
  * shift = beta - mean*scale, save_mean, save_invstd (each C floats) and, if

@@ -14,7 +14,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsifnn_b200.so")
-SOURCES = ["core.cu", "conv3x3.cu", "conv3x3_tc.cu", "wgrad.cu", "elementwise.cu", "loss.cu", "adam.cu", "modelb.cu"]
+SOURCES = ["core.cu", "conv3x3.cu", "conv3x3_tc.cu", "wgrad.cu", "wgrad_tc.cu", "elementwise.cu", "loss.cu", "adam.cu", "modelb.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared"]
 
@@ -31,7 +31,7 @@ def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"),
                                                         os.path.join(_HERE, "..", "include", "sifnn.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -73,6 +73,9 @@ SIGNATURES = {
     "sifnn_conv3x3_dgrad_border": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
     "sifnn_conv3x3_wgrad_workspace": (c_size_t, [c_int] * 5),
     "sifnn_conv3x3_wgrad": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
+    "sifnn_conv3x3_wgrad_tc_supported": (c_int, [c_int] * 4),
+    "sifnn_conv3x3_wgrad_tc_workspace": (c_size_t, [c_int] * 5),
+    "sifnn_conv3x3_wgrad_tc": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
     "sifnn_bn_train_finalize": (c_int, [c_void_p] * 9 + [c_int, c_double, c_void_p]),
     "sifnn_bn_eval_affine": (c_int, [c_void_p] * 6 + [c_int, c_void_p]),
     "sifnn_bn_relu_bwd_reduce": (c_int, [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),

@@ -304,36 +304,47 @@ __device__ __forceinline__ void cubic_coeffs(float t, float* c) {
     c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
+// grid = (ceil(H*W/4 / 256), B): each thread produces 4 consecutive output pixels (one float4 of each channel).  For a x4
+// up-sampling the four outputs of a source column j use source columns j-2..j+2 and the phases t = .625, .875, .125, .375.
 __global__ void __launch_bounds__(256) bicubic4_cat_kernel(const float* __restrict__ lst, const float* __restrict__ ndvi, float* __restrict__ xout,
-                                                           long long total, int h, int w) {
+                                                           int h, int w) {
     const int H = 4 * h, W = 4 * w;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % W);
-        const int y = (int)((idx / W) % H);
-        const long long b = idx / ((long long)W * H);
-        const float sy = ((float)y + 0.5f) * 0.25f - 0.5f, sx = ((float)x + 0.5f) * 0.25f - 0.5f;
-        const float fy = floorf(sy), fx = floorf(sx);
-        float cy[4], cx[4];
-        cubic_coeffs(sy - fy, cy);
-        cubic_coeffs(sx - fx, cx);
-        const int iy = (int)fy, ix = (int)fx;
-        const float* p = lst + (size_t)b * h * w;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= H * w) return;
+    const int y = t / w, j = t - y * w;
+    const int b = blockIdx.y;
+    const float sy = ((float)y + 0.5f) * 0.25f - 0.5f;
+    const float fy = floorf(sy);
+    float cy[4];
+    cubic_coeffs(sy - fy, cy);
+    const int iy = (int)fy;
+    const float* p = lst + (size_t)b * h * w;
+    // row-interpolated values at the 5 source columns j-2 .. j+2 (clamped)
+    float col[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+        const int xx = min(max(j - 2 + d, 0), w - 1);
         float acc = 0.f;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int yy = min(max(iy - 1 + a, 0), h - 1);
-            float row = 0.f;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                const int xx = min(max(ix - 1 + d, 0), w - 1);
-                row = fmaf(cx[d], __ldg(p + (size_t)yy * w + xx), row);
-            }
-            acc = fmaf(cy[a], row, acc);
+            acc = fmaf(cy[a], __ldg(p + (size_t)yy * w + xx), acc);
         }
-        const size_t o = (size_t)b * 2 * H * W + (size_t)y * W + x;
-        xout[o] = acc;
-        xout[o + (size_t)H * W] = __ldg(ndvi + (size_t)b * H * W + (size_t)y * W + x);
+        col[d] = acc;
     }
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float sx = ((float)(4 * j + i) + 0.5f) * 0.25f - 0.5f;
+        const float fx = floorf(sx);
+        float cx[4];
+        cubic_coeffs(sx - fx, cx);
+        const int base = (int)fx - 1 - (j - 2);  // 0 for i = 0,1 and 1 for i = 2,3
+        o[i] = cx[0] * col[base] + cx[1] * col[base + 1] + cx[2] * col[base + 2] + cx[3] * col[base + 3];
+    }
+    const size_t off = (size_t)b * 2 * H * W + (size_t)y * W + 4 * j;
+    *reinterpret_cast<float4*>(xout + off) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(xout + off + (size_t)H * W) = __ldg(reinterpret_cast<const float4*>(ndvi + (size_t)b * H * W + (size_t)y * W + 4 * j));
 }
 
 }  // namespace
@@ -440,8 +451,9 @@ extern "C" int sifnn_upcat_bwd(const float* dout, float* dlow, float* dskip, int
 
 extern "C" int sifnn_bicubic4_cat(const float* lst, const float* ndvi, float* x, int B, int h, int w, sifnn_stream_t stream) {
     SIFNN_REQUIRE(lst && ndvi && x && B > 0 && h > 0 && w > 0, "bicubic4_cat: bad arguments");
-    const long long total = (long long)B * 16 * h * w;
-    bicubic4_cat_kernel<<<grid_for(total, 256), 256, 0, sifnn::as_stream(stream)>>>(lst, ndvi, x, total, h, w);
+    SIFNN_REQUIRE(B <= 65535, "bicubic4_cat: batch too large");
+    dim3 grid((4 * h * w + 255) / 256, B);
+    bicubic4_cat_kernel<<<grid, 256, 0, sifnn::as_stream(stream)>>>(lst, ndvi, x, h, w);
     return sifnn::check_launch("bicubic4_cat_kernel");
 }
 

@@ -136,7 +136,9 @@ Workspace carve(const Net& n, void* base, int B, int H, int W, int train) {
         for (int i = 0; i < SIFNN_MODELB_NCONV; ++i) {
             const int s = n.conv[i].level;
             const size_t b = sifnn_conv3x3_wgrad_workspace(B, n.conv[i].cin, n.conv[i].cout, H >> s, W >> s);
+            const size_t b2 = sifnn_conv3x3_wgrad_tc_workspace(B, n.conv[i].cin, n.conv[i].cout, H >> s, W >> s);
             if (b > mx) mx = b;
+            if (b2 > mx) mx = b2;
         }
         w.wgrad_ws = c.take<char>(mx);
     }
@@ -278,6 +280,9 @@ extern "C" int sifnn_modelb_backward(const sifnn_modelb_cfg* cfg, const float* p
     // gradient of conv i's weights; input = raw[aff] through BN+ReLU, or a plain tensor
     auto wgrad = [&](int i, const float* in, int aff, const float* g) -> int {
         const ConvDesc& c = n.conv[i];
+        if (tc_enabled() && i != 17 && sifnn_conv3x3_wgrad_tc_supported(c.cin, c.cout, hs[c.level], ws[c.level]))
+            return sifnn_conv3x3_wgrad_tc(in, aff >= 0 ? sc(aff) : nullptr, aff >= 0 ? sh(aff) : nullptr, g, grads + n.w_off[i], w.wgrad_ws, B, c.cin,
+                                          c.cout, hs[c.level], ws[c.level], stream);
         return sifnn_conv3x3_wgrad(in, aff >= 0 ? sc(aff) : nullptr, aff >= 0 ? sh(aff) : nullptr, g, grads + n.w_off[i],
                                    i == 17 ? grads + n.bias_off : nullptr, w.wgrad_ws, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
     };

@@ -93,6 +93,21 @@ def conv3x3_wgrad(x, dy, in_scale=None, in_shift=None, want_bias: bool = False):
     return (dw, db) if want_bias else dw
 
 
+def conv3x3_wgrad_tc(x, dy, in_scale=None, in_shift=None):
+    """Weight gradient on the tcgen05 tensor cores (csrc/wgrad_tc.cu); same result contract as conv3x3_wgrad."""
+    _chk(x, dy, in_scale, in_shift)
+    B, Cin, H, W = x.shape
+    Cout = dy.shape[1]
+    lib = _lib.load()
+    if not lib.sifnn_conv3x3_wgrad_tc_supported(Cin, Cout, H, W):
+        raise _lib.SifnnError(f"conv3x3_wgrad_tc: unsupported shape Cin={Cin} Cout={Cout} H={H} W={W}")
+    nbytes = lib.sifnn_conv3x3_wgrad_tc_workspace(B, Cin, Cout, H, W)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    dw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
+    _lib.call("sifnn_conv3x3_wgrad_tc", _p(x), _p(in_scale), _p(in_shift), _p(dy), _p(dw), _p(ws), B, Cin, Cout, H, W, _s())
+    return dw
+
+
 def bn_train_finalize(stats, gamma, beta, n: float, running_mean=None, running_var=None):
     _chk(stats, gamma, beta, running_mean, running_var)
     C = gamma.numel()

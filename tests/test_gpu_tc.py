@@ -67,3 +67,42 @@ def test_tc_matches_simt_closely():
     x, w = rnd(2, 32, 32, 256, seed=11).cuda(), rnd(16, 32, 3, 3, seed=12, scale=0.2).cuda()
     a, b = ops.conv3x3_fwd(x, w), ops.conv3x3_fwd_tc(x, w)
     assert rel_err(b, a) < 5e-6
+
+
+def ref_wgrad(x, dy):
+    w = torch.zeros(dy.shape[1], x.shape[1], 3, 3, dtype=torch.float64, requires_grad=True)
+    (ref_conv(x, w) * dy.double()).sum().backward()
+    return w.grad
+
+
+WG_SHAPES = [(2, 16, 16, 8, 16), (1, 16, 16, 5, 32), (2, 32, 16, 8, 64), (2, 16, 32, 7, 48), (1, 32, 32, 12, 128), (2, 64, 32, 9, 64),
+             (1, 32, 64, 6, 32), (2, 128, 64, 5, 64), (3, 64, 64, 32, 32), (1, 16, 64, 3, 16), (2, 32, 16, 256, 256), (40, 16, 16, 64, 64)]
+
+
+@pytest.mark.parametrize("shape", WG_SHAPES)
+def test_tc_wgrad(shape):
+    B, Cin, Cout, H, W = shape
+    x, dy = rnd(B, Cin, H, W, seed=21), rnd(B, Cout, H, W, seed=22)
+    dw = ops.conv3x3_wgrad_tc(x.cuda(), dy.cuda())
+    assert rel_err(dw, ref_wgrad(x, dy)) < TOL
+    assert torch.equal(dw, ops.conv3x3_wgrad_tc(x.cuda(), dy.cuda()))  # deterministic reduction
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 8, 32), (2, 32, 16, 6, 64), (1, 64, 64, 8, 32), (2, 128, 64, 4, 64)])
+def test_tc_wgrad_affine(shape):
+    B, Cin, Cout, H, W = shape
+    x, dy = rnd(B, Cin, H, W, seed=23), rnd(B, Cout, H, W, seed=24)
+    sc, sh = 1 + 0.3 * rnd(Cin, seed=25), 0.2 * rnd(Cin, seed=26)
+    a = F.relu(x.double() * sc.double()[None, :, None, None] + sh.double()[None, :, None, None])
+    dw = ops.conv3x3_wgrad_tc(x.cuda(), dy.cuda(), sc.cuda(), sh.cuda())
+    assert rel_err(dw, ref_wgrad(a, dy)) < TOL
+
+
+def test_tc_wgrad_same_sign_sum_is_unbiased():
+    """All-positive operands: every product has the same sign, the worst case for the truncating tensor-core accumulator
+    (a long chain would drift by ~6e-8 per step); the rotating accumulator sets keep it inside the parity tolerance."""
+    B, Cin, Cout, H, W = 32, 16, 16, 256, 256
+    x, dy = rnd(B, Cin, H, W, seed=27).abs(), rnd(B, Cout, H, W, seed=28).abs()
+    dw = ops.conv3x3_wgrad_tc(x.cuda(), dy.cuda())
+    ref = ops.conv3x3_wgrad(x.cuda(), dy.cuda())
+    assert rel_err(dw, ref) < 1e-4 / 2
