@@ -196,7 +196,10 @@ def kernel_rooflines(batch, fp32_peak, tensor_peak_eff):
                 add("conv3x3_tc_kernel (dgrad)", timed(lambda: ops.conv3x3_dgrad_tc(dy, w)), fl)
             else:
                 add("conv3x3_kernel (dgrad, SIMT)", timed(lambda: ops.conv3x3_dgrad(dy, w)), fl)
-        add("wgrad_kernel (SIMT)", timed(lambda: ops.conv3x3_wgrad(x, dy, want_bias=(co == 1))), fl)
+        if use_tc and lib.sifnn_conv3x3_wgrad_tc_supported(ci, co, hw, hw):
+            add("wgrad_tc_kernel", timed(lambda: ops.conv3x3_wgrad_tc(x, dy)), fl)
+        else:
+            add("wgrad_kernel (SIMT)", timed(lambda: ops.conv3x3_wgrad(x, dy, want_bias=(co == 1))), fl)
         del x, dy, w
     out = []
     for name, (t, fl, n) in res.items():
@@ -330,7 +333,8 @@ def run_ours(args):
         traffic = None
         try:  # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
             import csv
-            name = "r1i_ncu_full_wgrad_16x16x256_summary.csv" if "wgrad" in top["kernel"] else "r1j_ncu_full_conv3x3_tc_64x32x128_summary.csv"
+            name = {"wgrad_tc_kernel": "r1k_ncu_full_wgrad_tc_32x16x256_summary.csv",
+                    "wgrad_kernel (SIMT)": "r1i_ncu_full_wgrad_16x16x256_summary.csv"}.get(top["kernel"], "r1j_ncu_full_conv3x3_tc_64x32x128_summary.csv")
             vals = {r[0]: r[1] for r in csv.reader(open(os.path.join(ROOT, "profiles", name))) if len(r) >= 2}
             traffic = {"bytes_per_launch": (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e6,
                        "launch": name.replace("_summary.csv", ""), "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum"}

@@ -525,6 +525,62 @@ __global__ void __launch_bounds__(128) dgrad_border_kernel(const float* __restri
     }
 }
 
+// Columns pass of the padding adjoint (modes 1 and 2 of dgrad_border_kernel), restructured around what bounds it: every dy element of
+// image column 0 / W-1 sits in its own 32-byte sector, so the pass is limited by the number of sector requests, not by bytes or FLOPs.
+// One CTA = (side, 32-row segment, image, 32 input channels): the dy column segment (all Cout channels, +1 halo row each way) and the
+// three weights of the side's kx for every (o, k) are staged in shared memory ONCE, lanes run along rows, warp w owns 4 input channels.
+// Mode 2 folds the corner cross terms in the same way wgrad_tc.cu folds the padding along x: row 0 meets dy[0] a second time through
+// the ky = 0 weight, row H-1 meets dy[H-1] a second time through the ky = 2 weight.
+constexpr int BCOL_ROWS = 32;
+__global__ void __launch_bounds__(256) dgrad_border_cols_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                                                                int Cin, int Cout, int H, int W, int corners) {
+    extern __shared__ __align__(16) float bsm[];
+    float* dys = bsm;                                   // [Cout][BCOL_ROWS + 2]: rows p0-1 .. p0+32
+    float* wsm = bsm + ((Cout * (BCOL_ROWS + 2) + 3) & ~3);  // [Cout][3 ky][32 k], 16-byte aligned
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int segs = (H + BCOL_ROWS - 1) / BCOL_ROWS;
+    const int side = blockIdx.x / segs;
+    const int p0 = (blockIdx.x % segs) * BCOL_ROWS;
+    const int b = blockIdx.y, kc0 = blockIdx.z * 32;
+    const int q = side ? W - 1 : 0, kx = side ? 2 : 0;
+    const size_t plane = (size_t)H * W;
+    const float* dyb = dy + (size_t)b * Cout * plane + q;
+    for (int idx = tid; idx < Cout * (BCOL_ROWS + 2); idx += 256) {
+        const int o = idx / (BCOL_ROWS + 2), r = idx - o * (BCOL_ROWS + 2);
+        const int y = p0 - 1 + r;
+        dys[idx] = (y >= 0 && y < H) ? __ldg(dyb + (size_t)o * plane + (size_t)y * W) : 0.f;
+    }
+    for (int idx = tid; idx < Cout * 96; idx += 256) {
+        const int k = idx & 31, ky = (idx >> 5) % 3, o = idx / 96;
+        wsm[idx] = (kc0 + k < Cin) ? __ldg(w + ((size_t)o * Cin + kc0 + k) * 9 + ky * 3 + kx) : 0.f;
+    }
+    __syncthreads();
+    const int p = p0 + lane;
+    const bool top = corners && p == 0, bot = corners && p == H - 1;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int o = 0; o < Cout; ++o) {
+        const float* dr = dys + o * (BCOL_ROWS + 2) + lane;   // dr[0] = dy[p-1], dr[1] = dy[p], dr[2] = dy[p+1]
+        const float dc = dr[1];
+        const float d0 = top ? dr[2] + dc : dr[2];            // ky = 0 reads row p+1
+        const float d2 = bot ? dr[0] + dc : dr[0];            // ky = 2 reads row p-1
+        const float4 w0 = *reinterpret_cast<const float4*>(wsm + o * 96 + 4 * warp);
+        const float4 w1 = *reinterpret_cast<const float4*>(wsm + o * 96 + 32 + 4 * warp);
+        const float4 w2 = *reinterpret_cast<const float4*>(wsm + o * 96 + 64 + 4 * warp);
+        acc[0] = fmaf(w0.x, d0, fmaf(w1.x, dc, fmaf(w2.x, d2, acc[0])));
+        acc[1] = fmaf(w0.y, d0, fmaf(w1.y, dc, fmaf(w2.y, d2, acc[1])));
+        acc[2] = fmaf(w0.z, d0, fmaf(w1.z, dc, fmaf(w2.z, d2, acc[2])));
+        acc[3] = fmaf(w0.w, d0, fmaf(w1.w, dc, fmaf(w2.w, d2, acc[3])));
+    }
+    if (p < H) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = kc0 + 4 * warp + u;
+            if (k < Cin) dx[((size_t)b * Cin + k) * plane + (size_t)p * W + q] += acc[u];
+        }
+    }
+}
+
 template <int CPT, int WARPS_CO, int PAD, bool AFFINE>
 int launch_conv(const ConvArgs& a0, cudaStream_t st) {
     constexpr int WARPS_ROW = 8 / WARPS_CO;
@@ -585,6 +641,17 @@ extern "C" int sifnn_conv3x3_dgrad(const float* dy, const float* w, float* dx, i
 }
 
 static int launch_border(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H, int W, int mode, cudaStream_t st) {
+    if (mode != 0) {
+        const size_t smem = ((size_t)((Cout * (BCOL_ROWS + 2) + 3) & ~3) + (size_t)Cout * 96) * sizeof(float);
+        static size_t smem_set = 48 * 1024;
+        if (smem > smem_set) {
+            SIFNN_CUDA(cudaFuncSetAttribute(dgrad_border_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+        }
+        dim3 grid(2 * ((H + BCOL_ROWS - 1) / BCOL_ROWS), B, (Cin + 31) / 32);
+        dgrad_border_cols_kernel<<<grid, 256, smem, st>>>(dy, w, dx, Cin, Cout, H, W, mode == 2 ? 1 : 0);
+        return sifnn::check_launch("dgrad_border_cols_kernel");
+    }
     const int L = mode ? H : W;
     dim3 grid(2 * ((L + 31) / 32), B, (Cin + BORDER_KC - 1) / BORDER_KC);
     dgrad_border_kernel<<<grid, 128, 0, st>>>(dy, w, dx, Cin, Cout, H, W, mode);

@@ -281,6 +281,71 @@ __global__ void __launch_bounds__(256) upcat_bwd_low_kernel(const float* __restr
     }
 }
 
+// Same adjoint, tiled: one CTA = (plane, band of 8 low-resolution rows).  The 20 contributing rows of dout are staged in shared memory with
+// coalesced float4 loads, reduced along x (6-tap gather per low-resolution column, weights computed once per thread) and then along y.
+// W <= 128 and W a power of two (the decoder's 32 / 64 / 128); other shapes take the generic kernel above.
+constexpr int UPB_TL = 8, UPB_NR = 2 * UPB_TL + 4;
+__device__ __forceinline__ void up_gather_weights(int i, int n_in, float r, float* wv) {
+    // weight of output index 2i-2+t (t = 0..5) on low-resolution index i
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+        const int y = 2 * i - 2 + t;
+        float wgt = 0.f;
+        if (y >= 0 && y < 2 * n_in) {
+            const UpCoord u = up_coord(y, n_in, r);
+            if (u.i0 == i) wgt += u.w0;
+            if (u.i1 == i) wgt += u.w1;
+        }
+        wv[t] = wgt;
+    }
+}
+__global__ void __launch_bounds__(256) upcat_bwd_low_tiled_kernel(const float* __restrict__ dout, float* __restrict__ dlow, int C1, int C2, int H, int W,
+                                                                  float ry, float rx) {
+    extern __shared__ __align__(16) float usm[];
+    const int Wo = 2 * W, Ho = 2 * H;
+    float* in_s = usm;                    // [UPB_NR][Wo + 4]: column x at index x + 2 (two zero columns each side)
+    float* tmp = usm + UPB_NR * (Wo + 4);  // [UPB_NR][W]
+    const int tid = threadIdx.x;
+    const int plane = blockIdx.y;          // b * C1 + c
+    const int b = plane / C1, c = plane - b * C1;
+    const int i_lo = blockIdx.x * UPB_TL;
+    const int y_lo = 2 * i_lo - 2;
+    const float* g = dout + ((size_t)b * (C1 + C2) + c) * Ho * Wo;
+    const int Wq = Wo >> 2;
+    for (int idx = tid; idx < UPB_NR * Wq; idx += 256) {
+        const int r = idx / Wq, x4 = idx - r * Wq;
+        const int y = y_lo + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < Ho) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)y * Wo) + x4);
+        float* d = in_s + r * (Wo + 4) + 2 + 4 * x4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    if (tid < UPB_NR * 4) {
+        const int r = tid >> 2, e = tid & 3;
+        in_s[r * (Wo + 4) + (e < 2 ? e : Wo + e)] = 0.f;
+    }
+    __syncthreads();
+    const int k = tid & (W - 1), rg = tid / W, nrg = 256 / W;
+    float wx[6];
+    up_gather_weights(k, W, rx, wx);
+    for (int r = rg; r < UPB_NR; r += nrg) {
+        const float2* p = reinterpret_cast<const float2*>(in_s + r * (Wo + 4) + 2 * k);   // columns 2k-2 .. 2k+3
+        const float2 a0 = p[0], a1 = p[1], a2 = p[2];
+        tmp[r * W + k] = fmaf(wx[0], a0.x, fmaf(wx[1], a0.y, fmaf(wx[2], a1.x, fmaf(wx[3], a1.y, fmaf(wx[4], a2.x, wx[5] * a2.y)))));
+    }
+    __syncthreads();
+    for (int il = rg; il < UPB_TL; il += nrg) {
+        const int i = i_lo + il;
+        if (i >= H) break;
+        float wy[6];
+        up_gather_weights(i, H, ry, wy);
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) acc = fmaf(wy[t], tmp[(2 * il + t) * W + k], acc);
+        dlow[((size_t)plane * H + i) * W + k] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(256) upcat_bwd_skip_kernel(const float* __restrict__ dout, float* __restrict__ dskip, long long total4,
                                                              int C1, int C2, int HWo4) {
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
@@ -441,8 +506,15 @@ extern "C" int sifnn_upcat_bwd(const float* dout, float* dlow, float* dskip, int
     SIFNN_REQUIRE(B > 0 && C1 > 0 && C2 > 0 && H > 0 && W > 0 && (H * W) % 1 == 0, "upcat_bwd: bad shape");
     cudaStream_t st = sifnn::as_stream(stream);
     const long long total = (long long)B * C1 * H * W;
-    upcat_bwd_low_kernel<<<grid_for(total, 256), 256, 0, st>>>(dout, dlow, total, C1, C2, H, W, up_ratio(H), up_ratio(W));
-    SIFNN_TRY(sifnn::check_launch("upcat_bwd_low_kernel"));
+    if (W <= 128 && W >= 8 && (W & (W - 1)) == 0 && (long long)B * C1 <= 65535) {
+        const size_t smem = (size_t)UPB_NR * (2 * W + 4 + W) * sizeof(float);
+        dim3 grid((H + UPB_TL - 1) / UPB_TL, B * C1);
+        upcat_bwd_low_tiled_kernel<<<grid, 256, smem, st>>>(dout, dlow, C1, C2, H, W, up_ratio(H), up_ratio(W));
+        SIFNN_TRY(sifnn::check_launch("upcat_bwd_low_tiled_kernel"));
+    } else {
+        upcat_bwd_low_kernel<<<grid_for(total, 256), 256, 0, st>>>(dout, dlow, total, C1, C2, H, W, up_ratio(H), up_ratio(W));
+        SIFNN_TRY(sifnn::check_launch("upcat_bwd_low_kernel"));
+    }
     const int HWo4 = H * W;  // (2H*2W)/4
     const long long total4 = (long long)B * C2 * HWo4;
     upcat_bwd_skip_kernel<<<grid_for(total4, 256), 256, 0, st>>>(dout, dskip, total4, C1, C2, HWo4);
