@@ -126,4 +126,17 @@ inline bool encode_planes_map(CUtensorMap* tmap, const float* base, int W, int H
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// same tensor with the plane index as the MIDDLE dimension, {W, planes, H}: a box {bw columns, bp planes, bh rows} lands in shared memory
+// as [row][plane][column], i.e. the channels of one image row are bw floats apart (coordinates: x, plane, y)
+inline bool encode_rows_of_planes_map(CUtensorMap* tmap, const float* base, int W, int H, long long planes, int bw, int bp, int bh) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)planes, (cuuint64_t)H};
+    const cuuint64_t gstride[2] = {(cuuint64_t)W * H * 4, (cuuint64_t)W * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bp, (cuuint32_t)bh};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace sifnn_tc

@@ -67,8 +67,8 @@ struct WtcSmem {
     static constexpr int A_TILE = TROWS * WT * 32;           // floats per hi (or lo) tile  [TROWS][WT][32 ch] (KC = 16: row r | row r+1)
     static constexpr int B_TILE = R * G * WT * 32;           // floats                      [R][G][WT][32]: n = (s*3 + kx)*N + o = 32 g + slot
     static constexpr int STAGE = 2 * A_TILE + B_TILE;
-    static constexpr int RAW_X = KC * TROWS * WT;            // [KC][TROWS][WT]
-    static constexpr int RAW_DY = N * R * DYW;               // [N][R][DYW]
+    static constexpr int RAW_X = KC * TROWS * WT;            // [TROWS][KC][WT]   (channels of a row WT floats apart)
+    static constexpr int RAW_DY = N * R * DYW;               // [R][N][DYW]
     static constexpr int RAW_STAGE = RAW_X + RAW_DY;
     static constexpr int RAW_STAGES = 2;
     static constexpr int CTRL_FLOATS = 256;                  // barriers, TMEM slot, BatchNorm scale/shift of the KC channels
@@ -143,8 +143,8 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
             if (lane == 0) {
                 float* dst = raw0 + (size_t)rs * SM::RAW_STAGE;
                 mbar_arrive_expect_tx(raw_full + rs, SM::RAW_STAGE * 4);
-                tma_load_3d(dst, &tmap_x, x0, y0 - 1, b * a.K + c0, raw_full + rs);
-                tma_load_3d(dst + SM::RAW_X, &tmap_dy, x0 - 4, y0, b * a.O, raw_full + rs);
+                tma_load_3d(dst, &tmap_x, x0, b * a.K + c0, y0 - 1, raw_full + rs);
+                tma_load_3d(dst + SM::RAW_X, &tmap_dy, x0 - 4, b * a.O, y0, raw_full + rs);
             }
             __syncwarp();
         }
@@ -192,11 +192,32 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
         __syncwarp();
     } else {
         // ======================= transformers =======================
+        // Work items are (row, 8-channel chunk, half X, column): lane bits = column & 3, X, column >> 2; the warp index and the iteration give the
+        // chunk and the row, so column, X and chunk -- hence the four channels, their BatchNorm affine and every address term but the row --
+        // are per-thread constants.  The slot <-> channel assignment inside a chunk is chosen for the shared-memory banks:
+        //   input:  slot 8*Q2 + 4*X + e  <->  channel 8*Q2 + 2*e + X             (raw rows are [channel][16 cols]: X shifts the bank by 16)
+        //   dy:     slot 8*Q2 + 4*X + e  <->  channel 8*Q2 + (e & 1) + 4*(e >> 1) + 2*X   (raw rows are [channel][24 cols]: +2 channels = +16 banks)
+        // so both the scalar reads (16 columns x 2 halves = 32 banks) and the 16-byte stores (8 lanes of a wavefront = 4 swizzled chunks x 2
+        // halves) are conflict-free.  The drain undoes the permutation.
         const int xt = tid - WTC_XF_WARP0 * 32;
+        const int xw = xt >> 5;
+        const int col = (xt & 3) | (((xt >> 3) & 3) << 2);
+        const int X = (xt >> 2) & 1;
+        static_assert(WT == 16, "lane mapping of the transformers assumes 16-column tiles");
         constexpr int ITEMS_A = TROWS * Q * WT;   // (row, channel quad, column)
         constexpr int NIT_A = (ITEMS_A + WTC_XF_THREADS - 1) / WTC_XF_THREADS;
         constexpr int ITEMS_B = R * OQ * WT;
         constexpr int NIT_B = (ITEMS_B + WTC_XF_THREADS - 1) / WTC_XF_THREADS;
+        constexpr int QH = Q / 2, OQH = OQ / 2;   // 8-channel chunks
+        const int Q2 = xw % QH, rrA0 = xw / QH;
+        const int O2 = xw % OQH, rB0 = xw / OQH;
+        float sc[4], sh[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { sc[e] = AFFINE ? sc_s[8 * Q2 + 2 * e + X] : 1.f; sh[e] = AFFINE ? sh_s[8 * Q2 + 2 * e + X] : 0.f; }
+        const int a_src = (8 * Q2 + X) * WT + col;                                       // + rj * KC * WT + 2 * e * WT
+        const int a_dst = col * 32 + ((Q2 ^ (col & 3)) << 3) + 4 * X;                    // + rr * WT * 32
+        const int a_dst2 = col * 32 + (((2 + Q2) ^ (col & 3)) << 3) + 4 * X;             // KC = 16: slots 16..31 of the line above
+        const int b_src = (8 * O2 + 2 * X) * DYW + 4 + col;                              // + r * N * DYW + ((e & 1) + 4 * (e >> 1)) * DYW
         int g = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++g) {
             int b, y0, x0;
@@ -210,52 +231,41 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
             if (g >= S) mbar_wait(ab_empty + s, ((g / S) - 1) & 1);
             mbar_wait(raw_full + rs, (g / RS) & 1);
             // ---- input tile: pixel lines [row][col][32 floats], 32-byte chunks XOR-permuted by (col & 3); rows clamped onto the image
-            //      (replicate padding along y).  Lane bits: col & 3, q & 1, col >> 2  ->  the 8 lanes of a store wavefront hit 8 different 16-byte bank groups.
+            //      (replicate padding along y)
 #pragma unroll
             for (int i = 0; i < NIT_A; ++i) {
-                const int item = xt + i * WTC_XF_THREADS;
-                if (ITEMS_A % WTC_XF_THREADS == 0 || item < ITEMS_A) {
-                    const int col = (item & 3) | (((item >> 3) % (WT / 4)) << 2);
-                    const int rest = item / (2 * WT);
-                    const int q = (((item >> 2) & 1) | ((rest % (Q / 2)) << 1));
-                    const int rr = rest / (Q / 2);
+                const int rr = rrA0 + i * (8 / QH);
+                if (ITEMS_A % WTC_XF_THREADS == 0 || rr < TROWS) {
                     const int rj = min(max(y0 + rr - 1, 0), H - 1) - (y0 - 1);
+                    const float* src = rawx + rj * (KC * WT) + a_src;
                     float hi[4], lo[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float t = rawx[((4 * q + e) * TROWS + rj) * WT + col];
-                        if (AFFINE) t = sifnn::act_affine_relu(t, sc_s[4 * q + e], sh_s[4 * q + e]);
+                        float t = src[2 * e * WT];
+                        if (AFFINE) t = sifnn::act_affine_relu(t, sc[e], sh[e]);
                         hi[e] = tf32_hi(t);
                         lo[e] = t - hi[e];
                     }
                     const float4 vh = make_float4(hi[0], hi[1], hi[2], hi[3]), vl = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                    {
-                        const int o = (rr * WT + col) * 32 + ((((4 * q) >> 3) ^ (col & 3)) << 3) + ((4 * q) & 7);
-                        *reinterpret_cast<float4*>(a_hi + o) = vh;
-                        *reinterpret_cast<float4*>(a_lo + o) = vl;
-                    }
+                    *reinterpret_cast<float4*>(a_hi + rr * (WT * 32) + a_dst) = vh;
+                    *reinterpret_cast<float4*>(a_lo + rr * (WT * 32) + a_dst) = vl;
                     if (KC == 16 && rr >= 1) {  // second copy: slots 16..31 of the line of the row above
-                        const int sl = 16 + 4 * q;
-                        const int o = ((rr - 1) * WT + col) * 32 + (((sl >> 3) ^ (col & 3)) << 3) + (sl & 7);
-                        *reinterpret_cast<float4*>(a_hi + o) = vh;
-                        *reinterpret_cast<float4*>(a_lo + o) = vl;
+                        *reinterpret_cast<float4*>(a_hi + (rr - 1) * (WT * 32) + a_dst2) = vh;
+                        *reinterpret_cast<float4*>(a_lo + (rr - 1) * (WT * 32) + a_dst2) = vl;
                     }
                 }
             }
-            // ---- dy tile: [row][group][col][32 slots], n = (s*3 + kx)*N + o: three column-shifted copies (replicate padding along x folded in), hi | lo
+            // ---- dy tile: [row][group][col][32 slots], n = (s*3 + kx)*N + o-slot: three column-shifted copies (replicate padding along x folded in), hi | lo
+            const int gx = x0 + col;
 #pragma unroll
             for (int i = 0; i < NIT_B; ++i) {
-                const int item = xt + i * WTC_XF_THREADS;
-                if (ITEMS_B % WTC_XF_THREADS == 0 || item < ITEMS_B) {
-                    const int col = (item & 3) | (((item >> 3) % (WT / 4)) << 2);
-                    const int rest = item / (2 * WT);
-                    const int oq = (((item >> 2) & 1) | ((rest % (OQ / 2)) << 1));
-                    const int r = rest / (OQ / 2);
-                    const int gx = x0 + col;
+                const int r = rB0 + i * (8 / OQH);
+                if (ITEMS_B % WTC_XF_THREADS == 0 || r < R) {
+                    const float* src = rawd + r * (N * DYW) + b_src;
                     float v[3][4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float* p = rawd + ((4 * oq + e) * R + r) * DYW + 4 + col;
+                        const float* p = src + ((e & 1) + 4 * (e >> 1)) * DYW;
                         const float dm = p[-1], dc = p[0], dp = p[1];
                         v[0][e] = (gx == 0) ? dp + dc : dp;
                         v[1][e] = dc;
@@ -268,8 +278,9 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
                         for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(v[kx][e]); lo[e] = v[kx][e] - hi[e]; }
 #pragma unroll
                         for (int sp = 0; sp < 2; ++sp) {
-                            const int n = (sp * 3 + kx) * N + 4 * oq;
-                            const int o = ((r * G + (n >> 5)) * WT + col) * 32 + ((((n & 31) >> 3) ^ (col & 3)) << 3) + (n & 7);
+                            const int n0 = (sp * 3 + kx) * N;   // compile-time; + 8 * O2 + 4 * X
+                            const int n = n0 + 8 * O2;
+                            const int o = ((r * G + (n >> 5)) * WT + col) * 32 + ((((n & 31) >> 3) ^ (col & 3)) << 3) + 4 * X;
                             *reinterpret_cast<float4*>(bt + o) = sp ? make_float4(lo[0], lo[1], lo[2], lo[3]) : make_float4(hi[0], hi[1], hi[2], hi[3]);
                         }
                     }
@@ -290,6 +301,7 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
         // ky' = lane quadrant, c = lane within the quadrant.
         const int quad = warp & 3, half = warp >> 2;
         const bool ok = (quad < 3) && (lane < KC);
+        const int cch = (lane & ~7) + 2 * (lane & 3) + ((lane >> 2) & 1);   // input slot -> channel
         constexpr int NB = 3 * N / 8;           // 8-column blocks of one accumulator half
 #pragma unroll 1
         for (int nb = half; nb < NB; nb += 2) {
@@ -310,8 +322,9 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int n = nb * 8 + j;       // n = kx * N + o
-                    const int kx = n / N, o = n - kx * N;
-                    a.partial[(((size_t)blockIdx.x * a.O + o) * a.K + c0 + lane) * 9 + quad * 3 + kx] = acc[j];
+                    const int kx = n / N, os = n - kx * N;
+                    const int o = (os & ~7) + (os & 1) + 4 * ((os >> 1) & 1) + 2 * ((os >> 2) & 1);   // dy slot -> channel
+                    a.partial[(((size_t)blockIdx.x * a.O + o) * a.K + c0 + cch) * 9 + quad * 3 + kx] = acc[j];
                 }
             }
         }
@@ -357,8 +370,8 @@ int launch_wtc(const float* in, const float* dy, WtcArgs a, int& S, bool affine,
     a.tiles_y = (a.H + R - 1) / R;
     a.num_tiles = a.B * a.tiles_x * a.tiles_y;
     CUtensorMap tx, td;
-    SIFNN_REQUIRE(encode_planes_map(&tx, in, a.W, a.H, (long long)a.B * a.K, WT, R + 2, KC) &&
-                      encode_planes_map(&td, dy, a.W, a.H, (long long)a.B * a.O, WT + 8, R, N),
+    SIFNN_REQUIRE(encode_rows_of_planes_map(&tx, in, a.W, a.H, (long long)a.B * a.K, WT, KC, R + 2) &&
+                      encode_rows_of_planes_map(&td, dy, a.W, a.H, (long long)a.B * a.O, WT + 8, N, R),
                   "conv3x3_wgrad_tc: cuTensorMapEncodeTiled is unavailable or failed");
     if (S > a.num_tiles) S = a.num_tiles;   // the caller reduces over the S partial slices actually written
     dim3 grid(S, a.K / KC);
