@@ -20,6 +20,8 @@
 //   tcgen05.commit; warps 0..7 then read the accumulators back (tcgen05.ld) for the epilogue.
 #include "tc_common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 using namespace sifnn_tc;
@@ -367,12 +369,20 @@ int launch_tc(const TcArgs& a0, cudaStream_t st) {
     return sifnn::check_launch("conv3x3_tc_kernel");
 }
 
+// 4 output rows per tile for the 128-pixel MMAs with <= 32 output channels (halo-row staging overhead 1.5x instead of 2x: 5-12 % faster,
+// profiles/r1m_conv3x3_tc_rows2_vs_rows4.log); SIFNN_TC_R4=0 restores 2 rows for A/B measurements.
+bool tc_rows4() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SIFNN_TC_R4"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 template <int PAD, bool AFFINE>
 int dispatch_tc(const TcArgs& a, cudaStream_t st) {
     if (a.W % 128 == 0) {
         switch (a.O) {
-            case 16: return launch_tc<16, 2, 128, PAD, AFFINE>(a, st);
-            case 32: return launch_tc<32, 2, 128, PAD, AFFINE>(a, st);
+            case 16: return tc_rows4() ? launch_tc<16, 4, 128, PAD, AFFINE>(a, st) : launch_tc<16, 2, 128, PAD, AFFINE>(a, st);
+            case 32: return tc_rows4() ? launch_tc<32, 4, 128, PAD, AFFINE>(a, st) : launch_tc<32, 2, 128, PAD, AFFINE>(a, st);
             case 64: return launch_tc<64, 2, 128, PAD, AFFINE>(a, st);
         }
     } else {  // 64-pixel-wide images: one image row per M = 64 MMA
