@@ -329,23 +329,425 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
     }
 }
 
-// Split the weights of one layer into TF32 hi / lo parts in the exact shared-memory image of a stage:
-// wprep[chunk][tap][q][row][e], row < N: hi of W[n = row][c = 8*chunk + 4q + e][tap], row >= N: lo of W[n = row - N].
-__global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wprep, int K, int N, int w_so, int w_sk, int flip) {
+// =====================================================================================================================
+// kx folded into N  (128-pixel MMAs, N <= 32 output channels)
+//
+// The 9-tap form above fetches a 4 KB activation tile from shared memory for every (tap, hi/lo) MMA while the MMA itself is only
+// 2N (N) columns wide: with 16 or 32 output channels the tensor core waits on its operand fetch.  Here the three kx taps of a
+// filter row are stacked along N instead:
+//
+//   E[pixel p][(s, kx, o)] += A[p][8 ch] * W[ky][(s, kx, o)][8 ch]        one MMA pair per (row, ky): 6 instead of 18 per chunk and row
+//   out[y][x][o] = E_kx0[x-1] + E_kx1[x] + E_kx2[x+1]                      (hi*hi block + cross block, summed by the epilogue)
+//
+// E_kx[p] depends on pixel p alone, so the tile has no halo columns, the kx shift becomes a +-1 LANE shift of the accumulator
+// (warp shuffles, quadrant edges through a small shared-memory exchange, tile edges carried from one tile to the next -- a CTA walks
+// the tiles of an image row in order), and padding is a rule on the edge term: replicate  E_kx0[-1] = E_kx0[0], E_kx2[W] = E_kx2[W-1];
+// zero (data gradient): both vanish.
+// TMEM: one row slot = 6N columns ([hi*hi : kx0 kx1 kx2][cross : kx0 kx1 kx2]), R slots used as a ring with per-row full/empty
+// barriers (the epilogue drains row r of tile i while the MMAs of rows r+1.. and of tile i+1 run), instead of two full sets.
+// =====================================================================================================================
+template <int N, int R>
+struct TcxSmem {
+    static constexpr int TROWS = R + 2;
+    static constexpr int A_TILE = 2 * TROWS * 128 * 4;          // floats per (hi or lo) tile: [2 q][TROWS*128 px][4]
+    static constexpr int B_TILE = 3 * 2 * 6 * N * 4;            // floats: [3 ky][2 q][6N rows = (s, kx, o)][4]
+    static constexpr int STAGE = 2 * A_TILE + B_TILE;
+    static constexpr int RAW_STAGE = TC_KC * TROWS * 128;       // floats
+    static constexpr int RAW_STAGES = 3;
+    static constexpr int CTRL_FLOATS = 512 + 2 * 2 * 4 * N + 2 * 2 * R * N;   // barriers / BatchNorm affine, edge exchange (2 buffers), tile carries (2 buffers)
+    static constexpr int CTRL_PAD = (CTRL_FLOATS + 31) / 32 * 32;
+    static constexpr int BUDGET = 222 * 1024;
+    static constexpr int REST = BUDGET - CTRL_PAD * 4 - RAW_STAGES * RAW_STAGE * 4;
+    static constexpr int STAGES = (STAGE * 4 * 4 <= REST) ? 4 : ((STAGE * 4 * 3 <= REST) ? 3 : 2);
+    static constexpr size_t BYTES = (size_t)(STAGES * STAGE + RAW_STAGES * RAW_STAGE + CTRL_PAD) * 4;
+    static constexpr int ROW_COLS = 6 * N;
+    static constexpr int TMEM_COLS = (R * ROW_COLS <= 128) ? 128 : (R * ROW_COLS <= 256) ? 256 : 512;
+    static_assert(R * ROW_COLS <= 512, "row slots must fit the 512 TMEM columns");
+    static_assert(STAGE * 4 * 2 <= REST, "two stages must fit");
+    static_assert((STAGE * 4) % 128 == 0 && (RAW_STAGE * 4) % 128 == 0 && (CTRL_PAD * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(6 * N <= 256 && R <= 4, "UMMA N limit / barrier slots");
+};
+
+template <int N, int R, int PAD, bool AFFINE>
+__global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
+    using SM = TcxSmem<N, R>;
+    constexpr int TROWS = SM::TROWS;
+    constexpr bool STATS = (PAD == 0);
+    constexpr int S = SM::STAGES;
+    constexpr int RS = SM::RAW_STAGES;
+    extern __shared__ __align__(128) float smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* ab_full = bars;            // [4]
+    uint64_t* ab_empty = bars + 4;       // [4]
+    uint64_t* raw_full = bars + 8;       // [4]
+    uint64_t* raw_empty = bars + 12;     // [4]
+    uint64_t* acc_full = bars + 16;      // [R <= 4]
+    uint64_t* acc_empty = bars + 20;     // [R <= 4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    float* sc_s = smem + 64;    // [<=128]
+    float* sh_s = smem + 192;   // [<=128]
+    float* xch = smem + 512;                     // [2 buffers][2: e0 of lane 31 | e2 of lane 0][4 quadrants][N]
+    float* carry_e0 = xch + 2 * 2 * 4 * N;       // [2][R][N]: E_kx0 of the last pixel of the previous tile of this image row (buffer = tile parity)
+    float* carry_out = carry_e0 + 2 * R * N;     // [2][R][N]: the unfinished output of that pixel
+    float* stage0 = smem + SM::CTRL_PAD;
+    float* raw0 = stage0 + (size_t)S * SM::STAGE;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = a.H, W = a.W, K = a.K;
+    const size_t plane = (size_t)H * W;
+    const int nchunks = K / TC_KC;
+    const int tiles_x = a.tiles_x;
+    const int tiles_per_img = tiles_x * a.tiles_y;
+    const int ngroups = a.num_tiles / tiles_x;   // a CTA owns whole row groups: the tiles_x tiles of R image rows, walked left to right
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(ab_full + s, TC_XF_THREADS / 32 + 1); mbar_init(ab_empty + s, 1); }   // one arrival per warp
+        for (int s = 0; s < RS; ++s) { mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, TC_XF_THREADS / 32); }
+        for (int s = 0; s < R; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, TC_EPI_WARPS); }
+        fence_mbar_init();
+    }
+    if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, SM::TMEM_COLS);
+    if (AFFINE) {
+        for (int i = tid; i < K; i += TC_THREADS2) { sc_s[i] = __ldg(a.in_scale + i); sh_s[i] = __ldg(a.in_shift + i); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_coords = [&](int tile, int& b, int& y0, int& x0) {
+        b = tile / tiles_per_img;
+        const int t = tile - b * tiles_per_img;
+        const int ty = t / tiles_x;
+        y0 = ty * R;
+        x0 = (t - ty * tiles_x) * 128;
+    };
+
+    if (warp == TC_LOAD_WARP) {
+        // ======================= loader: one TMA box (8 ch x TROWS rows x 128 cols) per chunk =======================
+        int g = 0;
+        for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+            for (int tx = 0; tx < tiles_x; ++tx) {
+                int b, y0, x0;
+                tile_coords(grp * tiles_x + tx, b, y0, x0);
+                for (int ch = 0; ch < nchunks; ++ch, ++g) {
+                    const int rs = g % RS;
+                    if (g >= RS) mbar_wait(raw_empty + rs, ((g / RS) - 1) & 1);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(raw_full + rs, SM::RAW_STAGE * 4);
+                        tma_load_3d(raw0 + (size_t)rs * SM::RAW_STAGE, &tmap, x0, y0 - 1, b * K + ch * TC_KC, raw_full + rs);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == TC_MMA_WARP) {
+        // ======================= MMA issuer (one thread) =======================
+        constexpr uint32_t idesc1 = make_idesc(128, 6 * N);  // a_hi x [w_hi(kx0..2) ; w_lo(kx0..2)]
+        constexpr uint32_t idesc2 = make_idesc(128, 3 * N);  // a_lo x  w_hi(kx0..2)
+        int g = 0, it = 0;
+        for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+            for (int tx = 0; tx < tiles_x; ++tx, ++it) {
+                int b, y0, x0;
+                tile_coords(grp * tiles_x + tx, b, y0, x0);
+                for (int ch = 0; ch < nchunks; ++ch, ++g) {
+                    const int s = g % S;
+                    mbar_wait(ab_full + s, (g / S) & 1);
+                    tc_fence_after();
+                    constexpr uint32_t LBO_A = TROWS * 128 * 16, LBO_B = 6 * N * 16, SBO = 128;
+                    const uint32_t a_hi = smem_u32(stage0 + (size_t)s * SM::STAGE);
+                    const uint64_t da_hi = make_desc(a_hi, LBO_A, SBO);
+                    const uint64_t da_lo = da_hi + (uint64_t)(SM::A_TILE * 4 / 16);
+                    const uint64_t db = da_hi + (uint64_t)(2 * SM::A_TILE * 4 / 16) - ((uint64_t)(LBO_A >> 4) << 16) + ((uint64_t)(LBO_B >> 4) << 16);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (lane == 0) {
+                            if (ch == 0 && it >= 1) {   // row slot r still holds the previous tile until its epilogue has drained it
+                                mbar_wait(acc_empty + r, (it - 1) & 1);
+                                tc_fence_after();
+                            }
+                            const uint32_t d = tmem_base + r * SM::ROW_COLS;
+#pragma unroll
+                            for (int ky = 0; ky < 3; ++ky) {
+                                const uint64_t oa = (uint64_t)((r + ky) * 128);  // 16-byte units
+                                const uint64_t ob = (uint64_t)(ky * 2 * 6 * N);
+                                umma_tf32(d, da_hi + oa, db + ob, idesc1, (ky == 0 && ch == 0) ? 0u : 1u);
+                                umma_tf32(d + 3 * N, da_lo + oa, db + ob, idesc2, 1u);
+                            }
+                            if (PAD == 1) {
+                                // Adjoint of the forward's replicate padding along y: the first (last) image row receives its own dy row a second
+                                // time through the ky = 0 (ky = 2) weights, i.e. the flipped filter row 2 (0), on the tile row of the output row itself.
+                                const int y = y0 + r;
+                                if (y == 0 || y == H - 1) {
+                                    const uint64_t oa = (uint64_t)((r + 1) * 128);
+                                    const uint64_t ob = (uint64_t)(((y == 0) ? 2 : 0) * 2 * 6 * N);
+                                    umma_tf32(d, da_hi + oa, db + ob, idesc1, 1u);
+                                    umma_tf32(d + 3 * N, da_lo + oa, db + ob, idesc2, 1u);
+                                    if (H == 1) {   // a one-row image is both first and last
+                                        const uint64_t ob2 = 0;
+                                        umma_tf32(d, da_hi + oa, db + ob2, idesc1, 1u);
+                                        umma_tf32(d + 3 * N, da_lo + oa, db + ob2, idesc2, 1u);
+                                    }
+                                }
+                            }
+                            if (ch == nchunks - 1) umma_commit(acc_full + r);   // row slot complete
+                        }
+                        __syncwarp();
+                    }
+                    if (lane == 0) umma_commit(ab_empty + s);                   // stage reusable once these MMAs have read it
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= TC_XF_WARP0) {
+        // ======================= transformers: raw -> BN/ReLU -> TF32 hi/lo pixel-major tiles (no halo columns) =======================
+        const int xt = tid - TC_XF_WARP0 * 32;
+        constexpr int ITEMS = 2 * TROWS * 128;
+        constexpr int NIT = ITEMS / TC_XF_THREADS;
+        static_assert(ITEMS % TC_XF_THREADS == 0, "whole items per thread");
+        int g = 0;
+        for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+            for (int tx = 0; tx < tiles_x; ++tx) {
+                int b, y0, x0;
+                tile_coords(grp * tiles_x + tx, b, y0, x0);
+                for (int ch = 0; ch < nchunks; ++ch, ++g) {
+                    const int s = g % S, rs = g % RS;
+                    float* a_hi = stage0 + (size_t)s * SM::STAGE;
+                    float* a_lo = a_hi + SM::A_TILE;
+                    const float* raw = raw0 + (size_t)rs * SM::RAW_STAGE;
+                    if (g >= S) mbar_wait(ab_empty + s, ((g / S) - 1) & 1);
+                    if (xt == 0) {  // weights of this chunk: one bulk copy straight into the stage
+                        mbar_arrive_expect_tx(ab_full + s, SM::B_TILE * 4);
+                        bulk_g2s(a_lo + SM::A_TILE, a.wprep + (size_t)ch * SM::B_TILE, SM::B_TILE * 4, ab_full + s);
+                    }
+                    mbar_wait(raw_full + rs, (g / RS) & 1);
+                    const int c0 = ch * TC_KC;
+#pragma unroll
+                    for (int i = 0; i < NIT; ++i) {
+                        const int item = xt + i * TC_XF_THREADS;       // (q, row, pixel)
+                        const int px = item & 127;
+                        const int rr = (item >> 7) % TROWS;
+                        const int q = item / (128 * TROWS);
+                        int rj = rr;
+                        if (PAD == 0) rj = min(max(y0 + rr - 1, 0), H - 1) - (y0 - 1);   // replicate padding along y
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float t = raw[((4 * q + e) * TROWS + rj) * 128 + px];
+                            if (AFFINE) t = sifnn::act_affine_relu(t, sc_s[c0 + 4 * q + e], sh_s[c0 + 4 * q + e]);
+                            hi[e] = tf32_hi(t);
+                            lo[e] = t - hi[e];
+                        }
+                        *reinterpret_cast<float4*>(a_hi + (size_t)item * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4*>(a_lo + (size_t)item * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    fence_proxy_async();           // this thread's st.shared -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if ((xt & 31) == 0) {          // one arrival per warp: 8 instead of 256 atomics on the barrier word
+                        mbar_arrive(raw_empty + rs);
+                        mbar_arrive(ab_full + s);
+                    }
+                }
+            }
+        }
+    } else {
+        // ======================= epilogue: TMEM -> lane-shifted sum over kx -> global (+ BatchNorm statistics) =======================
+        // The eight epilogue warps are the critical path of this kernel once the operand fetch is cut threefold, so the per-row code is
+        // kept lean: everything that depends only on the thread (channel base, exchange slots) is hoisted, the common path (31 of 32
+        // lanes on each side) is straight-line shuffles and adds, and the edge lanes patch their neighbour terms in two short branches.
+        const int quad = warp & 3, half = warp >> 2;
+        constexpr int NH = N / 2;                    // channels of this warp: [half * NH, half * NH + NH)
+        constexpr int NB = NH / 8;
+        const int nbase = half * NH;
+        float s1[STATS ? NH : 1], s2[STATS ? NH : 1];
+#pragma unroll
+        for (int j = 0; j < (STATS ? NH : 1); ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+        const bool accum = a.accumulate != 0, has_bias = a.bias != nullptr;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + nbase;
+        int it = 0, rowcnt = 0;
+        for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+            for (int tx = 0; tx < tiles_x; ++tx, ++it) {
+                int b, y0, x0;
+                tile_coords(grp * tiles_x + tx, b, y0, x0);
+                const bool img_left = (x0 == 0), img_right = (x0 + 128 == W);
+                const bool take_carry = (!img_left) && quad == 0;     // warp-uniform; lane 0 finishes the previous tile's last pixel
+                const bool defer = (!img_right) && quad == 3;         // warp-uniform; lane 31's right neighbour lives in the next tile
+                float* orow = a.out + ((size_t)b * a.O + nbase) * plane + (size_t)y0 * W + x0 + quad * 32 + lane;
+#pragma unroll 1
+                for (int r = 0; r < R; ++r, ++rowcnt, orow += W) {
+                    mbar_wait(acc_full + r, it & 1);
+                    tc_fence_after();
+                    float e0[NH], e1[NH], e2[NH];
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        const uint32_t taddr = tlane + r * SM::ROW_COLS + nb * 8;
+                        float h0[8], h1[8], h2[8], c0[8], c1[8], c2[8];
+                        tmem_ld8(taddr, h0); tmem_ld8(taddr + N, h1); tmem_ld8(taddr + 2 * N, h2);
+                        tmem_ld8(taddr + 3 * N, c0); tmem_ld8(taddr + 4 * N, c1); tmem_ld8(taddr + 5 * N, c2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { e0[nb * 8 + j] = h0[j] + c0[j]; e1[nb * 8 + j] = h1[j] + c1[j]; e2[nb * 8 + j] = h2[j] + c2[j]; }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + r);   // row slot may be overwritten by the next tile (one arrival per warp)
+                    // quadrant edges: lane 31 publishes its E_kx0 (the right neighbour's left term), lane 0 its E_kx2
+                    float* xb = xch + (rowcnt & 1) * (2 * 4 * N) + quad * N + nbase;
+                    if (lane == 31) {
+#pragma unroll
+                        for (int j = 0; j < NH; j += 4) *reinterpret_cast<float4*>(xb + j) = make_float4(e0[j], e0[j + 1], e0[j + 2], e0[j + 3]);
+                    } else if (lane == 0) {
+#pragma unroll
+                        for (int j = 0; j < NH; j += 4) *reinterpret_cast<float4*>(xb + 4 * N + j) = make_float4(e2[j], e2[j + 1], e2[j + 2], e2[j + 3]);
+                    }
+                    // tile carries alternate between two buffers by tile parity: this tile reads what the previous one wrote R rows (>= 1 barrier) ago
+                    const float* cin_e0 = carry_e0 + (((it + 1) & 1) * R + r) * N + nbase;
+                    const float* cin_out = carry_out + (((it + 1) & 1) * R + r) * N + nbase;
+                    float* cout_e0 = carry_e0 + ((it & 1) * R + r) * N + nbase;
+                    float* cout_out = carry_out + ((it & 1) * R + r) * N + nbase;
+                    asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+                    // in-place lane shift: e0 <- left neighbour's E_kx0, e2 <- right neighbour's E_kx2.  Lane 0 (31) keeps its own value, which is
+                    // exactly the replicate-padding rule at the image edge; elsewhere the edge lanes patch the term in below.
+#pragma unroll
+                    for (int j = 0; j < NH; ++j) {
+                        e0[j] = __shfl_up_sync(0xffffffffu, e0[j], 1);
+                        e2[j] = __shfl_down_sync(0xffffffffu, e2[j], 1);
+                    }
+                    if (lane == 0) {
+                        if (quad > 0) {
+#pragma unroll
+                            for (int j = 0; j < NH; ++j) e0[j] = xb[j - N];
+                        } else if (!img_left) {
+#pragma unroll
+                            for (int j = 0; j < NH; ++j) e0[j] = cin_e0[j];
+                        } else if (PAD == 1) {
+#pragma unroll
+                            for (int j = 0; j < NH; ++j) e0[j] = 0.f;
+                        }
+                    } else if (lane == 31) {
+                        if (quad < 3) {
+#pragma unroll
+                            for (int j = 0; j < NH; ++j) e2[j] = xb[4 * N + N + j];
+                        } else if (!img_right || PAD == 1) {   // deferred to the next tile, or zero padding
+#pragma unroll
+                            for (int j = 0; j < NH; ++j) e2[j] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NH; ++j) e1[j] += e0[j] + e2[j];
+                    float* const v = e1;
+                    if (y0 + r < H) {
+                        if (defer && lane == 31) {
+#pragma unroll
+                            for (int j = 0; j < NH; ++j) { cout_out[j] = v[j]; cout_e0[j] = xb[j]; }   // xb[j]: this lane's own E_kx0, published above
+                        } else {
+                            float* op = orow;
+#pragma unroll
+                            for (int j = 0; j < NH; ++j, op += plane) {
+                                float o = v[j];
+                                if (has_bias) o += __ldg(a.bias + nbase + j);
+                                if (accum) o += *op;
+                                *op = o;
+                                if (STATS) { s1[j] += o; s2[j] = fmaf(o, o, s2[j]); }
+                            }
+                        }
+                        if (take_carry && lane == 0) {   // finish pixel x0 - 1 (the last pixel of the previous tile of this row)
+                            float* op = orow - 1;
+#pragma unroll
+                            for (int j = 0; j < NH; ++j, op += plane) {
+                                float o = cin_out[j] + xb[4 * N + j];   // + this pixel's own E_kx2 (published above)
+                                if (has_bias) o += __ldg(a.bias + nbase + j);
+                                if (accum) o += *op;
+                                *op = o;
+                                if (STATS) { s1[j] += o; s2[j] = fmaf(o, o, s2[j]); }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (STATS && a.stats) {
+#pragma unroll
+            for (int j = 0; j < (STATS ? NH : 1); ++j) {
+                const float t1 = sifnn::warp_sum(s1[j]), t2 = sifnn::warp_sum(s2[j]);
+                if (lane == 0) {
+                    atomicAdd(a.stats + half * NH + j, (double)t1);
+                    atomicAdd(a.stats + a.O + half * NH + j, (double)t2);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, SM::TMEM_COLS);
+    }
+}
+
+// Split the weights of one layer into TF32 hi / lo parts in the exact shared-memory image of a stage.
+// fold = 0: wprep[chunk][tap][q][row][e], row < N: hi of W[n = row][c = 8*chunk + 4q + e][tap], row >= N: lo of W[n = row - N].
+// fold = 1: wprep[chunk][ky][q][row][e], row = (s * 3 + kx) * N + n  (hi rows of the three kx first, then the lo rows).
+__global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wprep, int K, int N, int w_so, int w_sk, int flip, int fold) {
     const int total = (K / 8) * 9 * 2 * 2 * N * 4;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int e = idx & 3;
-        const int row = (idx >> 2) % (2 * N);
-        const int q = ((idx >> 2) / (2 * N)) & 1;
-        const int t = ((idx >> 2) / (2 * N * 2)) % 9;
-        const int chunk = (idx >> 2) / (2 * N * 2 * 9);
-        const int n = row < N ? row : row - N;
+        int n, q, t, chunk, lo;
+        if (!fold) {
+            const int row = (idx >> 2) % (2 * N);
+            q = ((idx >> 2) / (2 * N)) & 1;
+            t = ((idx >> 2) / (2 * N * 2)) % 9;
+            chunk = (idx >> 2) / (2 * N * 2 * 9);
+            n = row < N ? row : row - N;
+            lo = row >= N;
+        } else {
+            const int row = (idx >> 2) % (6 * N);
+            q = ((idx >> 2) / (6 * N)) & 1;
+            const int ky = ((idx >> 2) / (6 * N * 2)) % 3;
+            chunk = (idx >> 2) / (6 * N * 2 * 3);
+            lo = row >= 3 * N;
+            const int rr = lo ? row - 3 * N : row;
+            t = ky * 3 + rr / N;
+            n = rr % N;
+        }
         const int c = chunk * 8 + 4 * q + e;
         const float v = __ldg(w + (size_t)n * w_so + (size_t)c * w_sk + (flip ? 8 - t : t));
         const float hi = tf32_hi(v);
-        wprep[idx] = row < N ? hi : v - hi;
+        wprep[idx] = lo ? v - hi : hi;
     }
 }
+
+template <int N, int R, int PAD, bool AFFINE>
+int launch_tcx(const TcArgs& a0, cudaStream_t st) {
+    using SM = TcxSmem<N, R>;
+    auto kern = conv3x3_tcx_kernel<N, R, PAD, AFFINE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
+        attr_done = true;
+    }
+    TcArgs a = a0;
+    a.tiles_x = a.W / 128;
+    a.tiles_y = (a.H + R - 1) / R;
+    a.num_tiles = a.B * a.tiles_x * a.tiles_y;
+    CUtensorMap tmap;
+    SIFNN_REQUIRE(encode_planes_map(&tmap, a.in, a.W, a.H, (long long)a.B * a.K, 128, R + 2, TC_KC),
+                  "conv3x3_tc: cuTensorMapEncodeTiled is unavailable or failed");
+    const int groups = a.num_tiles / a.tiles_x;
+    const int grid = groups < sifnn::num_sms() ? groups : sifnn::num_sms();
+    kern<<<grid, TC_THREADS2, SM::BYTES, st>>>(a, tmap);
+    return sifnn::check_launch("conv3x3_tcx_kernel");
+}
+
+// the kx-folded kernel serves the 128-pixel MMAs with <= 32 output channels; SIFNN_TC_KXFOLD=0 falls back to the 9-tap kernel (A/B runs)
+bool tc_fold_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SIFNN_TC_KXFOLD"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+// measured (profiles/r1n_conv3x3_tc_kxfold.log): 16 output channels gain 8-25 %; 32 output channels only break even from 64 input channels on
+// (two row slots fit the TMEM ring instead of four, and the epilogue works twice as long per row)
+bool tc_use_fold(int K, int O, int W) { return tc_fold_enabled() && (W % 128 == 0) && (O == 16 || (O == 32 && K >= 64)); }
 
 template <int N, int R, int MM, int PAD, bool AFFINE>
 int launch_tc(const TcArgs& a0, cudaStream_t st) {
@@ -379,6 +781,10 @@ bool tc_rows4() {
 
 template <int PAD, bool AFFINE>
 int dispatch_tc(const TcArgs& a, cudaStream_t st) {
+    if (tc_use_fold(a.K, a.O, a.W)) {
+        if (a.O == 16) return launch_tcx<16, 4, PAD, AFFINE>(a, st);
+        return launch_tcx<32, 2, PAD, AFFINE>(a, st);
+    }
     if (a.W % 128 == 0) {
         switch (a.O) {
             case 16: return tc_rows4() ? launch_tc<16, 4, 128, PAD, AFFINE>(a, st) : launch_tc<16, 2, 128, PAD, AFFINE>(a, st);
@@ -416,7 +822,7 @@ extern "C" int sifnn_conv3x3_fwd_tc(const float* in, const float* in_scale, cons
     SIFNN_REQUIRE(sifnn_conv3x3_tc_supported(Cin, Cout, H, W) && B > 0 && B <= 65535, "conv3x3_fwd_tc: unsupported shape Cin=%d Cout=%d H=%d W=%d", Cin, Cout, H, W);
     cudaStream_t st = sifnn::as_stream(stream);
     const int total = (Cin / 8) * 9 * 2 * 2 * Cout * 4;
-    tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, static_cast<float*>(wprep), Cin, Cout, Cin * 9, 9, 0);
+    tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, static_cast<float*>(wprep), Cin, Cout, Cin * 9, 9, 0, tc_use_fold(Cin, Cout, W) ? 1 : 0);
     SIFNN_TRY(sifnn::check_launch("tc_prep_weights_kernel"));
     TcArgs a{};
     a.in = in; a.in_scale = in_scale; a.in_shift = in_shift; a.wprep = static_cast<const float*>(wprep); a.bias = bias; a.out = out; a.stats = stats;
@@ -431,7 +837,7 @@ extern "C" int sifnn_conv3x3_dgrad_tc_main(const float* dy, const float* w, floa
     SIFNN_REQUIRE(sifnn_conv3x3_tc_supported(Cout, Cin, H, W) && B > 0 && B <= 65535, "conv3x3_dgrad_tc: unsupported shape");
     cudaStream_t st = sifnn::as_stream(stream);
     const int total = (Cout / 8) * 9 * 2 * 2 * Cin * 4;
-    tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, static_cast<float*>(wprep), Cout, Cin, 9, Cin * 9, 1);
+    tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, static_cast<float*>(wprep), Cout, Cin, 9, Cin * 9, 1, tc_use_fold(Cout, Cin, W) ? 1 : 0);
     SIFNN_TRY(sifnn::check_launch("tc_prep_weights_kernel"));
     TcArgs a{};
     a.in = dy; a.wprep = static_cast<const float*>(wprep); a.out = dx;
