@@ -43,7 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+    extra = os.environ.get("SIFNN_NVCC_EXTRA", "").split()   # e.g. -DSIFNN_MBAR_TEST_WAIT for A/B experiments
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB_PATH] + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

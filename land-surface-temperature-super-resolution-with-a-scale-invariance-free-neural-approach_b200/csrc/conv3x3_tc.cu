@@ -39,6 +39,7 @@ struct TcArgs {
     int B, K, O, H, W;
     int accumulate;
     int tiles_x, tiles_y, num_tiles;
+    int ablate;   // SIFNN_TC_ABLATE builds only: bit 0 no MMAs, 1 no output stores, 2 no transform, 3 no accumulator drain work
 };
 
 // Warp roles of the persistent kernel (18 warps)
@@ -354,24 +355,34 @@ struct TcxSmem {
     static constexpr int STAGE = 2 * A_TILE + B_TILE;
     static constexpr int RAW_STAGE = TC_KC * TROWS * 128;       // floats
     static constexpr int RAW_STAGES = 3;
-    static constexpr int CTRL_FLOATS = 512 + 2 * 2 * 4 * N + 2 * 2 * R * N;   // barriers / BatchNorm affine, edge exchange (2 buffers), tile carries (2 buffers)
+    static constexpr int CTRL_FLOATS = 512 + 2 * 2 * 2 * 4 * N + 2 * 2 * R * N;   // barriers / BatchNorm affine, edge exchange (2 buffers), tile carries (2 buffers)
     static constexpr int CTRL_PAD = (CTRL_FLOATS + 31) / 32 * 32;
     static constexpr int BUDGET = 222 * 1024;
     static constexpr int REST = BUDGET - CTRL_PAD * 4 - RAW_STAGES * RAW_STAGE * 4;
     static constexpr int STAGES = (STAGE * 4 * 4 <= REST) ? 4 : ((STAGE * 4 * 3 <= REST) ? 3 : 2);
     static constexpr size_t BYTES = (size_t)(STAGES * STAGE + RAW_STAGES * RAW_STAGE + CTRL_PAD) * 4;
     static constexpr int ROW_COLS = 6 * N;
-    static constexpr int TMEM_COLS = (R * ROW_COLS <= 128) ? 128 : (R * ROW_COLS <= 256) ? 256 : 512;
-    static_assert(R * ROW_COLS <= 512, "row slots must fit the 512 TMEM columns");
+    // Row slots of the TMEM ring: one MORE than the rows of a tile where it fits.  With exactly R slots the MMA of (tile i+1, row r)
+    // waits for the drain of (tile i, row r), which was committed only a few MMAs earlier: a barrier round trip (~1000 clocks) per row.
+    // The spare slot lets the issue thread run one row ahead of the drain.
+    static constexpr int NSLOT = ((R + 1) * ROW_COLS <= 512) ? R + 1 : R;
+    static constexpr int TMEM_COLS = 512;
+    static_assert(R * ROW_COLS <= 512 && NSLOT <= 5, "row slots must fit the 512 TMEM columns");
     static_assert(STAGE * 4 * 2 <= REST, "two stages must fit");
     static_assert((STAGE * 4) % 128 == 0 && (RAW_STAGE * 4) % 128 == 0 && (CTRL_PAD * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
     static_assert(6 * N <= 256 && R <= 4, "UMMA N limit / barrier slots");
 };
 
-template <int N, int R, int PAD, bool AFFINE>
-__global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
+// EW = number of epilogue warps: 8 (one group: TMEM lane quadrant = warp % 4, channel half = warp / 4, every row) or 16 (two such groups,
+// group g drains the rows r with r % 2 == g: two rows in flight, because a row's drain is one long latency chain -- barrier wake-up,
+// tcgen05.ld, named barrier, shuffles, stores).  With 16 epilogue warps the transformers get 4 warps instead of 8 (register budget).
+template <int N, int R, int PAD, bool AFFINE, int EW>
+__global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3_tcx_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
     using SM = TcxSmem<N, R>;
     constexpr int TROWS = SM::TROWS;
+    constexpr int XW = (EW == 16) ? 4 : 8, XF_T = XW * 32, EG = EW / 8;   // transformer warps / threads, epilogue row groups
+    constexpr int X_LOAD_WARP = EW, X_MMA_WARP = EW + 1, X_XF_WARP0 = EW + 2, X_THREADS = (EW + 2 + XW) * 32;
+    static_assert(R % EG == 0, "rows split evenly over the epilogue groups");
     constexpr bool STATS = (PAD == 0);
     constexpr int S = SM::STAGES;
     constexpr int RS = SM::RAW_STAGES;
@@ -381,13 +392,14 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
     uint64_t* ab_empty = bars + 4;       // [4]
     uint64_t* raw_full = bars + 8;       // [4]
     uint64_t* raw_empty = bars + 12;     // [4]
-    uint64_t* acc_full = bars + 16;      // [R <= 4]
-    uint64_t* acc_empty = bars + 20;     // [R <= 4]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    uint64_t* acc_full = bars + 16;      // [NSLOT <= 5]
+    uint64_t* acc_empty = bars + 22;     // [NSLOT <= 5]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    constexpr int NSLOT = SM::NSLOT;
     float* sc_s = smem + 64;    // [<=128]
     float* sh_s = smem + 192;   // [<=128]
-    float* xch = smem + 512;                     // [2 buffers][2: e0 of lane 31 | e2 of lane 0][4 quadrants][N]
-    float* carry_e0 = xch + 2 * 2 * 4 * N;       // [2][R][N]: E_kx0 of the last pixel of the previous tile of this image row (buffer = tile parity)
+    float* xch = smem + 512;                     // [2 groups][2 buffers][2: e0 of lane 31 | e2 of lane 0][4 quadrants][N]
+    float* carry_e0 = xch + 2 * 2 * 2 * 4 * N;       // [2][R][N]: E_kx0 of the last pixel of the previous tile of this image row (buffer = tile parity)
     float* carry_out = carry_e0 + 2 * R * N;     // [2][R][N]: the unfinished output of that pixel
     float* stage0 = smem + SM::CTRL_PAD;
     float* raw0 = stage0 + (size_t)S * SM::STAGE;
@@ -401,14 +413,14 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
     const int ngroups = a.num_tiles / tiles_x;   // a CTA owns whole row groups: the tiles_x tiles of R image rows, walked left to right
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(ab_full + s, TC_XF_THREADS / 32 + 1); mbar_init(ab_empty + s, 1); }   // one arrival per warp
-        for (int s = 0; s < RS; ++s) { mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, TC_XF_THREADS / 32); }
-        for (int s = 0; s < R; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, TC_EPI_WARPS); }
+        for (int s = 0; s < S; ++s) { mbar_init(ab_full + s, XW + 1); mbar_init(ab_empty + s, 1); }   // one arrival per warp
+        for (int s = 0; s < RS; ++s) { mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, XW); }
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 8); }
         fence_mbar_init();
     }
-    if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, SM::TMEM_COLS);
+    if (warp == X_MMA_WARP) tmem_alloc(tmem_slot, SM::TMEM_COLS);
     if (AFFINE) {
-        for (int i = tid; i < K; i += TC_THREADS2) { sc_s[i] = __ldg(a.in_scale + i); sh_s[i] = __ldg(a.in_shift + i); }
+        for (int i = tid; i < K; i += X_THREADS) { sc_s[i] = __ldg(a.in_scale + i); sh_s[i] = __ldg(a.in_shift + i); }
     }
     tc_fence_before();
     __syncthreads();
@@ -423,7 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
         x0 = (t - ty * tiles_x) * 128;
     };
 
-    if (warp == TC_LOAD_WARP) {
+    if (warp == X_LOAD_WARP) {
         // ======================= loader: one TMA box (8 ch x TROWS rows x 128 cols) per chunk =======================
         int g = 0;
         for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
@@ -432,7 +444,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
                 tile_coords(grp * tiles_x + tx, b, y0, x0);
                 for (int ch = 0; ch < nchunks; ++ch, ++g) {
                     const int rs = g % RS;
-                    if (g >= RS) mbar_wait(raw_empty + rs, ((g / RS) - 1) & 1);
+                    if (g >= RS) mbar_wait_warp(raw_empty + rs, ((g / RS) - 1) & 1);
                     if (lane == 0) {
                         mbar_arrive_expect_tx(raw_full + rs, SM::RAW_STAGE * 4);
                         tma_load_3d(raw0 + (size_t)rs * SM::RAW_STAGE, &tmap, x0, y0 - 1, b * K + ch * TC_KC, raw_full + rs);
@@ -441,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
                 }
             }
         }
-    } else if (warp == TC_MMA_WARP) {
+    } else if (warp == X_MMA_WARP) {
         // ======================= MMA issuer (one thread) =======================
         constexpr uint32_t idesc1 = make_idesc(128, 6 * N);  // a_hi x [w_hi(kx0..2) ; w_lo(kx0..2)]
         constexpr uint32_t idesc2 = make_idesc(128, 3 * N);  // a_lo x  w_hi(kx0..2)
@@ -462,11 +474,15 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         if (lane == 0) {
-                            if (ch == 0 && it >= 1) {   // row slot r still holds the previous tile until its epilogue has drained it
-                                mbar_wait(acc_empty + r, (it - 1) & 1);
+                            const int gr = it * R + r, slot = gr % NSLOT, use = gr / NSLOT;   // row slots are handed out round-robin
+                            if (ch == 0 && use >= 1) {   // the slot still holds an earlier row until the epilogue has drained it
+                                mbar_wait(acc_empty + slot, (use - 1) & 1);
                                 tc_fence_after();
                             }
-                            const uint32_t d = tmem_base + r * SM::ROW_COLS;
+                            const uint32_t d = tmem_base + slot * SM::ROW_COLS;
+#ifdef SIFNN_TC_ABLATE
+                            if (!(a.ablate & 1))
+#endif
 #pragma unroll
                             for (int ky = 0; ky < 3; ++ky) {
                                 const uint64_t oa = (uint64_t)((r + ky) * 128);  // 16-byte units
@@ -490,7 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
                                     }
                                 }
                             }
-                            if (ch == nchunks - 1) umma_commit(acc_full + r);   // row slot complete
+                            if (ch == nchunks - 1) umma_commit(acc_full + slot);   // row slot complete
                         }
                         __syncwarp();
                     }
@@ -499,12 +515,12 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
                 }
             }
         }
-    } else if (warp >= TC_XF_WARP0) {
+    } else if (warp >= X_XF_WARP0) {
         // ======================= transformers: raw -> BN/ReLU -> TF32 hi/lo pixel-major tiles (no halo columns) =======================
-        const int xt = tid - TC_XF_WARP0 * 32;
+        const int xt = tid - X_XF_WARP0 * 32;
         constexpr int ITEMS = 2 * TROWS * 128;
-        constexpr int NIT = ITEMS / TC_XF_THREADS;
-        static_assert(ITEMS % TC_XF_THREADS == 0, "whole items per thread");
+        constexpr int NIT = ITEMS / XF_T;
+        static_assert(ITEMS % XF_T == 0, "whole items per thread");
         int g = 0;
         for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
             for (int tx = 0; tx < tiles_x; ++tx) {
@@ -515,16 +531,19 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
                     float* a_hi = stage0 + (size_t)s * SM::STAGE;
                     float* a_lo = a_hi + SM::A_TILE;
                     const float* raw = raw0 + (size_t)rs * SM::RAW_STAGE;
-                    if (g >= S) mbar_wait(ab_empty + s, ((g / S) - 1) & 1);
+                    if (g >= S) mbar_wait_warp(ab_empty + s, ((g / S) - 1) & 1);
                     if (xt == 0) {  // weights of this chunk: one bulk copy straight into the stage
                         mbar_arrive_expect_tx(ab_full + s, SM::B_TILE * 4);
                         bulk_g2s(a_lo + SM::A_TILE, a.wprep + (size_t)ch * SM::B_TILE, SM::B_TILE * 4, ab_full + s);
                     }
-                    mbar_wait(raw_full + rs, (g / RS) & 1);
+                    mbar_wait_warp(raw_full + rs, (g / RS) & 1);
                     const int c0 = ch * TC_KC;
+#ifdef SIFNN_TC_ABLATE
+                    if (!(a.ablate & 4))
+#endif
 #pragma unroll
                     for (int i = 0; i < NIT; ++i) {
-                        const int item = xt + i * TC_XF_THREADS;       // (q, row, pixel)
+                        const int item = xt + i * XF_T;       // (q, row, pixel)
                         const int px = item & 127;
                         const int rr = (item >> 7) % TROWS;
                         const int q = item / (128 * TROWS);
@@ -555,9 +574,11 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
         // The eight epilogue warps are the critical path of this kernel once the operand fetch is cut threefold, so the per-row code is
         // kept lean: everything that depends only on the thread (channel base, exchange slots) is hoisted, the common path (31 of 32
         // lanes on each side) is straight-line shuffles and adds, and the edge lanes patch their neighbour terms in two short branches.
-        const int quad = warp & 3, half = warp >> 2;
+        const int quad = warp & 3, half = (warp >> 2) & 1, eg = warp >> 3;   // eg: row group of this warp
         constexpr int NH = N / 2;                    // channels of this warp: [half * NH, half * NH + NH)
-        constexpr int NB = NH / 8;
+        constexpr int LW = NH >= 8 ? 8 : 4;          // TMEM load width (columns)
+        constexpr int NB = NH / LW;
+        static_assert(NH % LW == 0 && NH % 4 == 0, "whole TMEM loads per warp");
         const int nbase = half * NH;
         float s1[STATS ? NH : 1], s2[STATS ? NH : 1];
 #pragma unroll
@@ -572,27 +593,36 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
                 const bool img_left = (x0 == 0), img_right = (x0 + 128 == W);
                 const bool take_carry = (!img_left) && quad == 0;     // warp-uniform; lane 0 finishes the previous tile's last pixel
                 const bool defer = (!img_right) && quad == 3;         // warp-uniform; lane 31's right neighbour lives in the next tile
-                float* orow = a.out + ((size_t)b * a.O + nbase) * plane + (size_t)y0 * W + x0 + quad * 32 + lane;
+                float* orow = a.out + ((size_t)b * a.O + nbase) * plane + (size_t)(y0 + eg) * W + x0 + quad * 32 + lane;
 #pragma unroll 1
-                for (int r = 0; r < R; ++r, ++rowcnt, orow += W) {
-                    mbar_wait(acc_full + r, it & 1);
+                for (int r = eg; r < R; r += EG, ++rowcnt, orow += EG * W) {
+                    const int gr = it * R + r, slot = gr % NSLOT;
+                    mbar_wait_warp(acc_full + slot, (gr / NSLOT) & 1);
                     tc_fence_after();
                     float e0[NH], e1[NH], e2[NH];
+#ifdef SIFNN_TC_ABLATE
+                    if (a.ablate & 8) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty + slot);
+                        continue;
+                    }
+#endif
 #pragma unroll
                     for (int nb = 0; nb < NB; ++nb) {
-                        const uint32_t taddr = tlane + r * SM::ROW_COLS + nb * 8;
-                        float h0[8], h1[8], h2[8], c0[8], c1[8], c2[8];
-                        tmem_ld8(taddr, h0); tmem_ld8(taddr + N, h1); tmem_ld8(taddr + 2 * N, h2);
-                        tmem_ld8(taddr + 3 * N, c0); tmem_ld8(taddr + 4 * N, c1); tmem_ld8(taddr + 5 * N, c2);
+                        const uint32_t taddr = tlane + slot * SM::ROW_COLS + nb * LW;
+                        float h0[LW], h1[LW], h2[LW], c0[LW], c1[LW], c2[LW];
+                        tmem_ldw<LW>(taddr, h0); tmem_ldw<LW>(taddr + N, h1); tmem_ldw<LW>(taddr + 2 * N, h2);
+                        tmem_ldw<LW>(taddr + 3 * N, c0); tmem_ldw<LW>(taddr + 4 * N, c1); tmem_ldw<LW>(taddr + 5 * N, c2);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { e0[nb * 8 + j] = h0[j] + c0[j]; e1[nb * 8 + j] = h1[j] + c1[j]; e2[nb * 8 + j] = h2[j] + c2[j]; }
+                        for (int j = 0; j < LW; ++j) { e0[nb * LW + j] = h0[j] + c0[j]; e1[nb * LW + j] = h1[j] + c1[j]; e2[nb * LW + j] = h2[j] + c2[j]; }
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty + r);   // row slot may be overwritten by the next tile (one arrival per warp)
+                    if (lane == 0) mbar_arrive(acc_empty + slot);   // the slot may be overwritten (one arrival per warp)
                     // quadrant edges: lane 31 publishes its E_kx0 (the right neighbour's left term), lane 0 its E_kx2
-                    float* xb = xch + (rowcnt & 1) * (2 * 4 * N) + quad * N + nbase;
+                    float* xb = xch + (eg * 2 + (rowcnt & 1)) * (2 * 4 * N) + quad * N + nbase;
                     if (lane == 31) {
 #pragma unroll
                         for (int j = 0; j < NH; j += 4) *reinterpret_cast<float4*>(xb + j) = make_float4(e0[j], e0[j + 1], e0[j + 2], e0[j + 3]);
@@ -605,7 +635,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
                     const float* cin_out = carry_out + (((it + 1) & 1) * R + r) * N + nbase;
                     float* cout_e0 = carry_e0 + ((it & 1) * R + r) * N + nbase;
                     float* cout_out = carry_out + ((it & 1) * R + r) * N + nbase;
-                    asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+                    asm volatile("bar.sync %0, 256;" ::"r"(1 + eg) : "memory");   // the 8 warps of this row group
                     // in-place lane shift: e0 <- left neighbour's E_kx0, e2 <- right neighbour's E_kx2.  Lane 0 (31) keeps its own value, which is
                     // exactly the replicate-padding rule at the image edge; elsewhere the edge lanes patch the term in below.
 #pragma unroll
@@ -636,6 +666,9 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
 #pragma unroll
                     for (int j = 0; j < NH; ++j) e1[j] += e0[j] + e2[j];
                     float* const v = e1;
+#ifdef SIFNN_TC_ABLATE
+                    if (a.ablate & 2) continue;
+#endif
                     if (y0 + r < H) {
                         if (defer && lane == 31) {
 #pragma unroll
@@ -679,7 +712,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tcx_kernel(const TcArg
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == TC_MMA_WARP) {
+    if (warp == X_MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, SM::TMEM_COLS);
     }
@@ -717,16 +750,17 @@ __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __res
     }
 }
 
-template <int N, int R, int PAD, bool AFFINE>
+template <int N, int R, int PAD, bool AFFINE, int EW>
 int launch_tcx(const TcArgs& a0, cudaStream_t st) {
     using SM = TcxSmem<N, R>;
-    auto kern = conv3x3_tcx_kernel<N, R, PAD, AFFINE>;
+    auto kern = conv3x3_tcx_kernel<N, R, PAD, AFFINE, EW>;
     static bool attr_done = false;
     if (!attr_done) {
         SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
         attr_done = true;
     }
     TcArgs a = a0;
+    { const char* e = getenv("SIFNN_TC_ABLATE"); a.ablate = e ? atoi(e) : 0; }
     a.tiles_x = a.W / 128;
     a.tiles_y = (a.H + R - 1) / R;
     a.num_tiles = a.B * a.tiles_x * a.tiles_y;
@@ -735,7 +769,7 @@ int launch_tcx(const TcArgs& a0, cudaStream_t st) {
                   "conv3x3_tc: cuTensorMapEncodeTiled is unavailable or failed");
     const int groups = a.num_tiles / a.tiles_x;
     const int grid = groups < sifnn::num_sms() ? groups : sifnn::num_sms();
-    kern<<<grid, TC_THREADS2, SM::BYTES, st>>>(a, tmap);
+    kern<<<grid, (EW + 2 + (EW == 16 ? 4 : 8)) * 32, SM::BYTES, st>>>(a, tmap);
     return sifnn::check_launch("conv3x3_tcx_kernel");
 }
 
@@ -747,6 +781,12 @@ bool tc_fold_enabled() {
 }
 // measured (profiles/r1n_conv3x3_tc_kxfold.log): 16 output channels gain 8-25 %; 32 output channels only break even from 64 input channels on
 // (two row slots fit the TMEM ring instead of four, and the epilogue works twice as long per row)
+// experiment switch: SIFNN_TC_EPI16=1 gives the kx-folded kernel 16 epilogue warps in two row groups
+bool tc_epi16() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SIFNN_TC_EPI16"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
 bool tc_use_fold(int K, int O, int W) { return tc_fold_enabled() && (W % 128 == 0) && (O == 16 || (O == 32 && K >= 64)); }
 
 template <int N, int R, int MM, int PAD, bool AFFINE>
@@ -782,8 +822,8 @@ bool tc_rows4() {
 template <int PAD, bool AFFINE>
 int dispatch_tc(const TcArgs& a, cudaStream_t st) {
     if (tc_use_fold(a.K, a.O, a.W)) {
-        if (a.O == 16) return launch_tcx<16, 4, PAD, AFFINE>(a, st);
-        return launch_tcx<32, 2, PAD, AFFINE>(a, st);
+        if (a.O == 16) return tc_epi16() ? launch_tcx<16, 4, PAD, AFFINE, 16>(a, st) : launch_tcx<16, 4, PAD, AFFINE, 8>(a, st);
+        return tc_epi16() ? launch_tcx<32, 2, PAD, AFFINE, 16>(a, st) : launch_tcx<32, 2, PAD, AFFINE, 8>(a, st);
     }
     if (a.W % 128 == 0) {
         switch (a.O) {
