@@ -347,20 +347,27 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
 // TMEM: one row slot = 6N columns ([hi*hi : kx0 kx1 kx2][cross : kx0 kx1 kx2]), R slots used as a ring with per-row full/empty
 // barriers (the epilogue drains row r of tile i while the MMAs of rows r+1.. and of tile i+1 run), instead of two full sets.
 // =====================================================================================================================
-template <int N, int R>
+// WCH > 0: the split weights of all WCH chunks stay resident in shared memory for the whole kernel (they are the same for every tile);
+// WCH == 0: each stage carries the weights of its chunk (more chunks than fit).
+template <int N, int R, int WCH>
 struct TcxSmem {
     static constexpr int TROWS = R + 2;
     static constexpr int A_TILE = 2 * TROWS * 128 * 4;          // floats per (hi or lo) tile: [2 q][TROWS*128 px][4]
     static constexpr int B_TILE = 3 * 2 * 6 * N * 4;            // floats: [3 ky][2 q][6N rows = (s, kx, o)][4]
-    static constexpr int STAGE = 2 * A_TILE + B_TILE;
+    static constexpr int STAGE = 2 * A_TILE + (WCH ? 0 : B_TILE);
+    static constexpr int W_ALL = WCH * B_TILE;                  // floats
     static constexpr int RAW_STAGE = TC_KC * TROWS * 128;       // floats
-    static constexpr int RAW_STAGES = 3;
     static constexpr int CTRL_FLOATS = 512 + 2 * 2 * 2 * 4 * N + 2 * 2 * R * N;   // barriers / BatchNorm affine, edge exchange (2 buffers), tile carries (2 buffers)
     static constexpr int CTRL_PAD = (CTRL_FLOATS + 31) / 32 * 32;
     static constexpr int BUDGET = 222 * 1024;
-    static constexpr int REST = BUDGET - CTRL_PAD * 4 - RAW_STAGES * RAW_STAGE * 4;
-    static constexpr int STAGES = (STAGE * 4 * 4 <= REST) ? 4 : ((STAGE * 4 * 3 <= REST) ? 3 : 2);
-    static constexpr size_t BYTES = (size_t)(STAGES * STAGE + RAW_STAGES * RAW_STAGE + CTRL_PAD) * 4;
+    // two transformed stages are enough (transform and MMA are short); everything left goes to raw boxes in flight (up to 4), which is what
+    // hides the load latency
+    static constexpr int STAGES = 2;
+    static constexpr int RAW_ROOM = (BUDGET - CTRL_PAD * 4 - W_ALL * 4 - STAGES * STAGE * 4) / (RAW_STAGE * 4);
+    static constexpr int RAW_STAGES = RAW_ROOM >= 4 ? 4 : RAW_ROOM;
+    static constexpr int REST = BUDGET - CTRL_PAD * 4 - RAW_STAGES * RAW_STAGE * 4 - W_ALL * 4;
+    static_assert(RAW_STAGES >= 2, "at least two raw boxes in flight");
+    static constexpr size_t BYTES = (size_t)(STAGES * STAGE + RAW_STAGES * RAW_STAGE + CTRL_PAD + W_ALL) * 4;
     static constexpr int ROW_COLS = 6 * N;
     // Row slots of the TMEM ring: one MORE than the rows of a tile where it fits.  With exactly R slots the MMA of (tile i+1, row r)
     // waits for the drain of (tile i, row r), which was committed only a few MMAs earlier: a barrier round trip (~1000 clocks) per row.
@@ -376,9 +383,9 @@ struct TcxSmem {
 // EW = number of epilogue warps: 8 (one group: TMEM lane quadrant = warp % 4, channel half = warp / 4, every row) or 16 (two such groups,
 // group g drains the rows r with r % 2 == g: two rows in flight, because a row's drain is one long latency chain -- barrier wake-up,
 // tcgen05.ld, named barrier, shuffles, stores).  With 16 epilogue warps the transformers get 4 warps instead of 8 (register budget).
-template <int N, int R, int PAD, bool AFFINE, int EW>
+template <int N, int R, int PAD, bool AFFINE, int EW, int WCH>
 __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3_tcx_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
-    using SM = TcxSmem<N, R>;
+    using SM = TcxSmem<N, R, WCH>;
     constexpr int TROWS = SM::TROWS;
     constexpr int XW = (EW == 16) ? 4 : 8, XF_T = XW * 32, EG = EW / 8;   // transformer warps / threads, epilogue row groups
     constexpr int X_LOAD_WARP = EW, X_MMA_WARP = EW + 1, X_XF_WARP0 = EW + 2, X_THREADS = (EW + 2 + XW) * 32;
@@ -395,6 +402,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
     uint64_t* acc_full = bars + 16;      // [NSLOT <= 5]
     uint64_t* acc_empty = bars + 22;     // [NSLOT <= 5]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    uint64_t* w_full = bars + 30;        // resident weights have landed (WCH > 0)
     constexpr int NSLOT = SM::NSLOT;
     float* sc_s = smem + 64;    // [<=128]
     float* sh_s = smem + 192;   // [<=128]
@@ -403,6 +411,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
     float* carry_out = carry_e0 + 2 * R * N;     // [2][R][N]: the unfinished output of that pixel
     float* stage0 = smem + SM::CTRL_PAD;
     float* raw0 = stage0 + (size_t)S * SM::STAGE;
+    float* wall = raw0 + (size_t)RS * SM::RAW_STAGE;   // [WCH][B_TILE] resident weights
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = a.H, W = a.W, K = a.K;
@@ -413,7 +422,8 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
     const int ngroups = a.num_tiles / tiles_x;   // a CTA owns whole row groups: the tiles_x tiles of R image rows, walked left to right
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(ab_full + s, XW + 1); mbar_init(ab_empty + s, 1); }   // one arrival per warp
+        for (int s = 0; s < S; ++s) { mbar_init(ab_full + s, XW + (WCH ? 0 : 1)); mbar_init(ab_empty + s, 1); }   // one arrival per warp
+        mbar_init(w_full, 1);
         for (int s = 0; s < RS; ++s) { mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, XW); }
         for (int s = 0; s < NSLOT; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 8); }
         fence_mbar_init();
@@ -426,6 +436,10 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (WCH > 0 && tid == 0) {   // all weights of the layer, once: one bulk copy
+        mbar_arrive_expect_tx(w_full, SM::W_ALL * 4);
+        bulk_g2s(wall, a.wprep, SM::W_ALL * 4, w_full);
+    }
 
     auto tile_coords = [&](int tile, int& b, int& y0, int& x0) {
         b = tile / tiles_per_img;
@@ -458,6 +472,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
         constexpr uint32_t idesc1 = make_idesc(128, 6 * N);  // a_hi x [w_hi(kx0..2) ; w_lo(kx0..2)]
         constexpr uint32_t idesc2 = make_idesc(128, 3 * N);  // a_lo x  w_hi(kx0..2)
         int g = 0, it = 0;
+        if (WCH > 0) mbar_wait(w_full, 0);
         for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
             for (int tx = 0; tx < tiles_x; ++tx, ++it) {
                 int b, y0, x0;
@@ -470,7 +485,8 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                     const uint32_t a_hi = smem_u32(stage0 + (size_t)s * SM::STAGE);
                     const uint64_t da_hi = make_desc(a_hi, LBO_A, SBO);
                     const uint64_t da_lo = da_hi + (uint64_t)(SM::A_TILE * 4 / 16);
-                    const uint64_t db = da_hi + (uint64_t)(2 * SM::A_TILE * 4 / 16) - ((uint64_t)(LBO_A >> 4) << 16) + ((uint64_t)(LBO_B >> 4) << 16);
+                    const uint64_t db = WCH ? make_desc(smem_u32(wall + (size_t)ch * SM::B_TILE), LBO_B, SBO)
+                                            : da_hi + (uint64_t)(2 * SM::A_TILE * 4 / 16) - ((uint64_t)(LBO_A >> 4) << 16) + ((uint64_t)(LBO_B >> 4) << 16);
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         if (lane == 0) {
@@ -532,7 +548,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                     float* a_lo = a_hi + SM::A_TILE;
                     const float* raw = raw0 + (size_t)rs * SM::RAW_STAGE;
                     if (g >= S) mbar_wait_warp(ab_empty + s, ((g / S) - 1) & 1);
-                    if (xt == 0) {  // weights of this chunk: one bulk copy straight into the stage
+                    if (WCH == 0 && xt == 0) {  // weights of this chunk: one bulk copy straight into the stage
                         mbar_arrive_expect_tx(ab_full + s, SM::B_TILE * 4);
                         bulk_g2s(a_lo + SM::A_TILE, a.wprep + (size_t)ch * SM::B_TILE, SM::B_TILE * 4, ab_full + s);
                     }
@@ -750,10 +766,10 @@ __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __res
     }
 }
 
-template <int N, int R, int PAD, bool AFFINE, int EW>
-int launch_tcx(const TcArgs& a0, cudaStream_t st) {
-    using SM = TcxSmem<N, R>;
-    auto kern = conv3x3_tcx_kernel<N, R, PAD, AFFINE, EW>;
+template <int N, int R, int PAD, bool AFFINE, int EW, int WCH>
+int launch_tcx_w(const TcArgs& a0, cudaStream_t st) {
+    using SM = TcxSmem<N, R, WCH>;
+    auto kern = conv3x3_tcx_kernel<N, R, PAD, AFFINE, EW, WCH>;
     static bool attr_done = false;
     if (!attr_done) {
         SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
@@ -771,6 +787,14 @@ int launch_tcx(const TcArgs& a0, cudaStream_t st) {
     const int grid = groups < sifnn::num_sms() ? groups : sifnn::num_sms();
     kern<<<grid, (EW + 2 + (EW == 16 ? 4 : 8)) * 32, SM::BYTES, st>>>(a, tmap);
     return sifnn::check_launch("conv3x3_tcx_kernel");
+}
+
+// resident weights when the layer has 2 or 4 chunks of input channels (16 / 32: every 16-output-channel use in ModelB)
+template <int N, int R, int PAD, bool AFFINE, int EW>
+int launch_tcx(const TcArgs& a, cudaStream_t st) {
+    if (N == 16 && a.K == 16) return launch_tcx_w<N, R, PAD, AFFINE, EW, (N == 16 ? 2 : 0)>(a, st);
+    if (N == 16 && a.K == 32) return launch_tcx_w<N, R, PAD, AFFINE, EW, (N == 16 ? 4 : 0)>(a, st);
+    return launch_tcx_w<N, R, PAD, AFFINE, EW, 0>(a, st);
 }
 
 // the kx-folded kernel serves the 128-pixel MMAs with <= 32 output channels; SIFNN_TC_KXFOLD=0 falls back to the 9-tap kernel (A/B runs)
