@@ -22,6 +22,14 @@
 
 #include <cstdlib>
 
+#ifdef SIFNN_TC_TRACE
+static unsigned long long* g_trace = nullptr;
+extern "C" void sifnn_debug_set_trace(void* p) { g_trace = static_cast<unsigned long long*>(p); }
+#define TC_STAMP(ev, idx) do { if (a.trace && blockIdx.x == 0 && (idx) < 64) a.trace[(ev) * 64 + (idx)] = clock64(); } while (0)
+#else
+#define TC_STAMP(ev, idx) do { } while (0)
+#endif
+
 namespace {
 
 using namespace sifnn_tc;
@@ -39,6 +47,7 @@ struct TcArgs {
     int B, K, O, H, W;
     int accumulate;
     int tiles_x, tiles_y, num_tiles;
+    unsigned long long* trace;   // SIFNN_TC_TRACE builds only: clock64 stamps of CTA 0, [event][slot], 64 slots per event
     int ablate;   // SIFNN_TC_ABLATE builds only: bit 0 no MMAs, 1 no output stores, 2 no transform, 3 no accumulator drain work
 };
 
@@ -460,6 +469,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                     const int rs = g % RS;
                     if (g >= RS) mbar_wait_warp(raw_empty + rs, ((g / RS) - 1) & 1);
                     if (lane == 0) {
+                        TC_STAMP(0, g);
                         mbar_arrive_expect_tx(raw_full + rs, SM::RAW_STAGE * 4);
                         tma_load_3d(raw0 + (size_t)rs * SM::RAW_STAGE, &tmap, x0, y0 - 1, b * K + ch * TC_KC, raw_full + rs);
                     }
@@ -481,6 +491,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                     const int s = g % S;
                     mbar_wait(ab_full + s, (g / S) & 1);
                     tc_fence_after();
+                    if (lane == 0) TC_STAMP(4, g);
                     constexpr uint32_t LBO_A = TROWS * 128 * 16, LBO_B = 6 * N * 16, SBO = 128;
                     const uint32_t a_hi = smem_u32(stage0 + (size_t)s * SM::STAGE);
                     const uint64_t da_hi = make_desc(a_hi, LBO_A, SBO);
@@ -495,6 +506,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                                 mbar_wait(acc_empty + slot, (use - 1) & 1);
                                 tc_fence_after();
                             }
+                            if (ch == 0) TC_STAMP(8, gr);
                             const uint32_t d = tmem_base + slot * SM::ROW_COLS;
 #ifdef SIFNN_TC_ABLATE
                             if (!(a.ablate & 1))
@@ -526,7 +538,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                         }
                         __syncwarp();
                     }
-                    if (lane == 0) umma_commit(ab_empty + s);                   // stage reusable once these MMAs have read it
+                    if (lane == 0) { TC_STAMP(5, g); umma_commit(ab_empty + s); }                   // stage reusable once these MMAs have read it
                     __syncwarp();
                 }
             }
@@ -548,11 +560,13 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                     float* a_lo = a_hi + SM::A_TILE;
                     const float* raw = raw0 + (size_t)rs * SM::RAW_STAGE;
                     if (g >= S) mbar_wait_warp(ab_empty + s, ((g / S) - 1) & 1);
+                    if (xt == 0) TC_STAMP(1, g);
                     if (WCH == 0 && xt == 0) {  // weights of this chunk: one bulk copy straight into the stage
                         mbar_arrive_expect_tx(ab_full + s, SM::B_TILE * 4);
                         bulk_g2s(a_lo + SM::A_TILE, a.wprep + (size_t)ch * SM::B_TILE, SM::B_TILE * 4, ab_full + s);
                     }
                     mbar_wait_warp(raw_full + rs, (g / RS) & 1);
+                    if (xt == 0) TC_STAMP(2, g);
                     const int c0 = ch * TC_KC;
 #ifdef SIFNN_TC_ABLATE
                     if (!(a.ablate & 4))
@@ -576,6 +590,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                         *reinterpret_cast<float4*>(a_hi + (size_t)item * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                         *reinterpret_cast<float4*>(a_lo + (size_t)item * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     }
+                    if (xt == 0) TC_STAMP(3, g);
                     fence_proxy_async();           // this thread's st.shared -> visible to the tensor core (async proxy)
                     __syncwarp();
                     if ((xt & 31) == 0) {          // one arrival per warp: 8 instead of 256 atomics on the barrier word
@@ -615,6 +630,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                     const int gr = it * R + r, slot = gr % NSLOT;
                     mbar_wait_warp(acc_full + slot, (gr / NSLOT) & 1);
                     tc_fence_after();
+                    if (tid == 0) TC_STAMP(6, gr);
                     float e0[NH], e1[NH], e2[NH];
 #ifdef SIFNN_TC_ABLATE
                     if (a.ablate & 8) {
@@ -685,6 +701,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
 #ifdef SIFNN_TC_ABLATE
                     if (a.ablate & 2) continue;
 #endif
+                    if (tid == 0) TC_STAMP(7, gr);
                     if (y0 + r < H) {
                         if (defer && lane == 31) {
 #pragma unroll
@@ -777,6 +794,9 @@ int launch_tcx_w(const TcArgs& a0, cudaStream_t st) {
     }
     TcArgs a = a0;
     { const char* e = getenv("SIFNN_TC_ABLATE"); a.ablate = e ? atoi(e) : 0; }
+#ifdef SIFNN_TC_TRACE
+    a.trace = g_trace;
+#endif
     a.tiles_x = a.W / 128;
     a.tiles_y = (a.H + R - 1) / R;
     a.num_tiles = a.B * a.tiles_x * a.tiles_y;

@@ -80,7 +80,7 @@ struct WtcSmem {
     static constexpr int NSETS = (512 / SET_COLS) >= 4 ? 4 : (512 / SET_COLS);
     static constexpr int KBLOCKS = R * (WT / 8);             // K steps (dy row, 8-column block) per tile
     static_assert(M == 64 || M == 128, "UMMA M");
-    static_assert(NSETS >= 1 && KBLOCKS % NSETS == 0, "the accumulator-set rotation must be static inside a tile");
+    static_assert(NSETS >= 1, "at least one accumulator set");
     static_assert(STAGE * 4 * 2 <= REST, "two pipeline stages must fit shared memory");
     static_assert((A_TILE * 4) % 1024 == 0 && (B_TILE * 4) % 1024 == 0, "swizzled tiles must stay 1 KB aligned");
     static_assert((RAW_X * 4) % 128 == 0 && (RAW_STAGE * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
@@ -165,14 +165,16 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
                 const uint64_t da_hi = make_desc(a_hi, LBO_A, SBO) | SW;
                 const uint64_t da_lo = da_hi + (uint64_t)(SM::A_TILE * 4 / 16);
                 const uint64_t db = (make_desc(a_hi, LBO_B, SBO) | SW) + (uint64_t)(2 * SM::A_TILE * 4 / 16);
-                const uint32_t first = (g != 0) ? 1u : 0u;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
 #pragma unroll
                     for (int j = 0; j < WT / 8; ++j) {
+                        // one accumulator set per TILE (rotating over the sets from tile to tile): switching the accumulator costs the tensor
+                        // core ~265 clocks, a follow-up MMA into the same one ~120 (tools/mma_cost_probe.cu), so the set changes 8x less often
+                        // than with a per-K-block rotation while the chain per set stays total / NSETS
                         const int kb = r * (WT / 8) + j;
-                        const uint32_t d = tmem_base + (uint32_t)((kb % SM::NSETS) * SM::SET_COLS);
-                        const uint32_t acc = (kb < SM::NSETS) ? first : 1u;
+                        const uint32_t d = tmem_base + (uint32_t)((g % SM::NSETS) * SM::SET_COLS);
+                        const uint32_t acc = (g < SM::NSETS && kb == 0) ? 0u : 1u;
                         const uint64_t oa = (uint64_t)((r * WT + 8 * j) * 8);          // 16-byte units (a pixel line is 128 B): tile row r = input row y-1 of dy row r
                         const uint64_t ob = (uint64_t)((r * G * WT + 8 * j) * 8);
                         if (SPLIT_N) {
@@ -301,6 +303,8 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
         // ky' = lane quadrant, c = lane within the quadrant.
         const int quad = warp & 3, half = warp >> 2;
         const bool ok = (quad < 3) && (lane < KC);
+        const int my_tiles = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int sets_used = my_tiles < SM::NSETS ? my_tiles : SM::NSETS;
         const int cch = (lane & ~7) + 2 * (lane & 3) + ((lane >> 2) & 1);   // input slot -> channel
         constexpr int NB = 3 * N / 8;           // 8-column blocks of one accumulator half
 #pragma unroll 1
@@ -310,6 +314,7 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
             for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
             for (int set = 0; set < SM::NSETS; ++set) {
+                if (set >= sets_used) break;   // a CTA with fewer tiles than sets never touched the others
                 float d1[8], d2[8];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + set * SM::SET_COLS + nb * 8;
                 tmem_ld8(taddr, d1);
