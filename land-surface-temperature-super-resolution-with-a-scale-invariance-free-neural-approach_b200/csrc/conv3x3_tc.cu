@@ -358,14 +358,16 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) conv3x3_tc_kernel(const TcArgs
 // =====================================================================================================================
 // WCH > 0: the split weights of all WCH chunks stay resident in shared memory for the whole kernel (they are the same for every tile);
 // WCH == 0: each stage carries the weights of its chunk (more chunks than fit).
-template <int N, int R, int WCH>
+// BF: 3-term BF16 split instead of TF32 (K = 16 channels per MMA and chunk: half the MMA instructions; opt-in)
+template <int N, int R, int WCH, bool BF = false>
 struct TcxSmem {
     static constexpr int TROWS = R + 2;
+    static constexpr int KC = BF ? 16 : TC_KC;                  // input channels per chunk
     static constexpr int A_TILE = 2 * TROWS * 128 * 4;          // floats per (hi or lo) tile: [2 q][TROWS*128 px][4]
     static constexpr int B_TILE = 3 * 2 * 6 * N * 4;            // floats: [3 ky][2 q][6N rows = (s, kx, o)][4]
     static constexpr int STAGE = 2 * A_TILE + (WCH ? 0 : B_TILE);
     static constexpr int W_ALL = WCH * B_TILE;                  // floats
-    static constexpr int RAW_STAGE = TC_KC * TROWS * 128;       // floats
+    static constexpr int RAW_STAGE = KC * TROWS * 128;          // floats
     static constexpr int CTRL_FLOATS = 512 + 2 * 2 * 2 * 4 * N + 2 * 2 * R * N;   // barriers / BatchNorm affine, edge exchange (2 buffers), tile carries (2 buffers)
     static constexpr int CTRL_PAD = (CTRL_FLOATS + 31) / 32 * 32;
     static constexpr int BUDGET = 222 * 1024;
@@ -392,9 +394,10 @@ struct TcxSmem {
 // EW = number of epilogue warps: 8 (one group: TMEM lane quadrant = warp % 4, channel half = warp / 4, every row) or 16 (two such groups,
 // group g drains the rows r with r % 2 == g: two rows in flight, because a row's drain is one long latency chain -- barrier wake-up,
 // tcgen05.ld, named barrier, shuffles, stores).  With 16 epilogue warps the transformers get 4 warps instead of 8 (register budget).
-template <int N, int R, int PAD, bool AFFINE, int EW, int WCH>
+template <int N, int R, int PAD, bool AFFINE, int EW, int WCH, bool BF>
 __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3_tcx_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
-    using SM = TcxSmem<N, R, WCH>;
+    using SM = TcxSmem<N, R, WCH, BF>;
+    constexpr int KC = SM::KC;
     constexpr int TROWS = SM::TROWS;
     constexpr int XW = (EW == 16) ? 4 : 8, XF_T = XW * 32, EG = EW / 8;   // transformer warps / threads, epilogue row groups
     constexpr int X_LOAD_WARP = EW, X_MMA_WARP = EW + 1, X_XF_WARP0 = EW + 2, X_THREADS = (EW + 2 + XW) * 32;
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = a.H, W = a.W, K = a.K;
     const size_t plane = (size_t)H * W;
-    const int nchunks = K / TC_KC;
+    const int nchunks = K / KC;
     const int tiles_x = a.tiles_x;
     const int tiles_per_img = tiles_x * a.tiles_y;
     const int ngroups = a.num_tiles / tiles_x;   // a CTA owns whole row groups: the tiles_x tiles of R image rows, walked left to right
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                     if (lane == 0) {
                         TC_STAMP(0, g);
                         mbar_arrive_expect_tx(raw_full + rs, SM::RAW_STAGE * 4);
-                        tma_load_3d(raw0 + (size_t)rs * SM::RAW_STAGE, &tmap, x0, y0 - 1, b * K + ch * TC_KC, raw_full + rs);
+                        tma_load_3d(raw0 + (size_t)rs * SM::RAW_STAGE, &tmap, x0, y0 - 1, b * K + ch * KC, raw_full + rs);
                     }
                     __syncwarp();
                 }
@@ -479,8 +482,9 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
         }
     } else if (warp == X_MMA_WARP) {
         // ======================= MMA issuer (one thread) =======================
-        constexpr uint32_t idesc1 = make_idesc(128, 6 * N);  // a_hi x [w_hi(kx0..2) ; w_lo(kx0..2)]
-        constexpr uint32_t idesc2 = make_idesc(128, 3 * N);  // a_lo x  w_hi(kx0..2)
+        constexpr uint32_t idesc1 = BF ? make_idesc_bf16(128, 6 * N) : make_idesc(128, 6 * N);  // a_hi x [w_hi(kx0..2) ; w_lo(kx0..2)]
+        constexpr uint32_t idesc2 = BF ? make_idesc_bf16(128, 3 * N) : make_idesc(128, 3 * N);  // a_lo x  w_hi(kx0..2)
+        auto mma = [](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) { if (BF) umma_bf16(d, da, db, id, acc); else umma_tf32(d, da, db, id, acc); };
         int g = 0, it = 0;
         if (WCH > 0) mbar_wait(w_full, 0);
         for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
@@ -515,8 +519,8 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                             for (int ky = 0; ky < 3; ++ky) {
                                 const uint64_t oa = (uint64_t)((r + ky) * 128);  // 16-byte units
                                 const uint64_t ob = (uint64_t)(ky * 2 * 6 * N);
-                                umma_tf32(d, da_hi + oa, db + ob, idesc1, (ky == 0 && ch == 0) ? 0u : 1u);
-                                umma_tf32(d + 3 * N, da_lo + oa, db + ob, idesc2, 1u);
+                                mma(d, da_hi + oa, db + ob, idesc1, (ky == 0 && ch == 0) ? 0u : 1u);
+                                mma(d + 3 * N, da_lo + oa, db + ob, idesc2, 1u);
                             }
                             if (PAD == 1) {
                                 // Adjoint of the forward's replicate padding along y: the first (last) image row receives its own dy row a second
@@ -525,12 +529,12 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                                 if (y == 0 || y == H - 1) {
                                     const uint64_t oa = (uint64_t)((r + 1) * 128);
                                     const uint64_t ob = (uint64_t)(((y == 0) ? 2 : 0) * 2 * 6 * N);
-                                    umma_tf32(d, da_hi + oa, db + ob, idesc1, 1u);
-                                    umma_tf32(d + 3 * N, da_lo + oa, db + ob, idesc2, 1u);
+                                    mma(d, da_hi + oa, db + ob, idesc1, 1u);
+                                    mma(d + 3 * N, da_lo + oa, db + ob, idesc2, 1u);
                                     if (H == 1) {   // a one-row image is both first and last
                                         const uint64_t ob2 = 0;
-                                        umma_tf32(d, da_hi + oa, db + ob2, idesc1, 1u);
-                                        umma_tf32(d + 3 * N, da_lo + oa, db + ob2, idesc2, 1u);
+                                        mma(d, da_hi + oa, db + ob2, idesc1, 1u);
+                                        mma(d + 3 * N, da_lo + oa, db + ob2, idesc2, 1u);
                                     }
                                 }
                             }
@@ -567,7 +571,7 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                     }
                     mbar_wait_warp(raw_full + rs, (g / RS) & 1);
                     if (xt == 0) TC_STAMP(2, g);
-                    const int c0 = ch * TC_KC;
+                    const int c0 = ch * KC;
 #ifdef SIFNN_TC_ABLATE
                     if (!(a.ablate & 4))
 #endif
@@ -579,16 +583,35 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
                         const int q = item / (128 * TROWS);
                         int rj = rr;
                         if (PAD == 0) rj = min(max(y0 + rr - 1, 0), H - 1) - (y0 - 1);   // replicate padding along y
-                        float hi[4], lo[4];
+                        if constexpr (!BF) {
+                            float hi[4], lo[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float t = raw[((4 * q + e) * TROWS + rj) * 128 + px];
-                            if (AFFINE) t = sifnn::act_affine_relu(t, sc_s[c0 + 4 * q + e], sh_s[c0 + 4 * q + e]);
-                            hi[e] = tf32_hi(t);
-                            lo[e] = t - hi[e];
+                            for (int e = 0; e < 4; ++e) {
+                                float t = raw[((4 * q + e) * TROWS + rj) * 128 + px];
+                                if (AFFINE) t = sifnn::act_affine_relu(t, sc_s[c0 + 4 * q + e], sh_s[c0 + 4 * q + e]);
+                                hi[e] = tf32_hi(t);
+                                lo[e] = t - hi[e];
+                            }
+                            *reinterpret_cast<float4*>(a_hi + (size_t)item * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<float4*>(a_lo + (size_t)item * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                        } else {   // 8 channels of one pixel -> one 16-byte unit of 8 BF16 (hi tile) and one of the residuals (lo tile)
+                            uint32_t hp[4], lp[4];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                unsigned short h0, l0, h1, l1;
+                                float t0 = raw[((8 * q + e) * TROWS + rj) * 128 + px], t1 = raw[((8 * q + e + 1) * TROWS + rj) * 128 + px];
+                                if (AFFINE) {
+                                    t0 = sifnn::act_affine_relu(t0, sc_s[c0 + 8 * q + e], sh_s[c0 + 8 * q + e]);
+                                    t1 = sifnn::act_affine_relu(t1, sc_s[c0 + 8 * q + e + 1], sh_s[c0 + 8 * q + e + 1]);
+                                }
+                                bf16_split(t0, h0, l0);
+                                bf16_split(t1, h1, l1);
+                                hp[e >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                                lp[e >> 1] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                            }
+                            *reinterpret_cast<uint4*>(a_hi + (size_t)item * 4) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                            *reinterpret_cast<uint4*>(a_lo + (size_t)item * 4) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
                         }
-                        *reinterpret_cast<float4*>(a_hi + (size_t)item * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<float4*>(a_lo + (size_t)item * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     }
                     if (xt == 0) TC_STAMP(3, g);
                     fence_proxy_async();           // this thread's st.shared -> visible to the tensor core (async proxy)
@@ -783,10 +806,30 @@ __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __res
     }
 }
 
-template <int N, int R, int PAD, bool AFFINE, int EW, int WCH>
+// BF16 variant of the fold layout: wprep[chunk of 16 ch][ky][q][row][8 bf16], row = (s * 3 + kx) * N + n, channel = 16*chunk + 8q + e
+__global__ void tc_prep_weights_bf16_kernel(const float* __restrict__ w, unsigned short* __restrict__ wprep, int K, int N, int w_so, int w_sk, int flip) {
+    const int total = (K / 16) * 3 * 2 * 6 * N * 8;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int e = idx & 7;
+        const int row = (idx >> 3) % (6 * N);
+        const int q = ((idx >> 3) / (6 * N)) & 1;
+        const int ky = ((idx >> 3) / (6 * N * 2)) % 3;
+        const int chunk = (idx >> 3) / (6 * N * 2 * 3);
+        const int lo = row >= 3 * N;
+        const int rr = lo ? row - 3 * N : row;
+        const int t = ky * 3 + rr / N, n = rr % N;
+        const int c = chunk * 16 + 8 * q + e;
+        const float v = __ldg(w + (size_t)n * w_so + (size_t)c * w_sk + (flip ? 8 - t : t));
+        unsigned short h, l;
+        bf16_split(v, h, l);
+        wprep[idx] = lo ? l : h;
+    }
+}
+
+template <int N, int R, int PAD, bool AFFINE, int EW, int WCH, bool BF>
 int launch_tcx_w(const TcArgs& a0, cudaStream_t st) {
-    using SM = TcxSmem<N, R, WCH>;
-    auto kern = conv3x3_tcx_kernel<N, R, PAD, AFFINE, EW, WCH>;
+    using SM = TcxSmem<N, R, WCH, BF>;
+    auto kern = conv3x3_tcx_kernel<N, R, PAD, AFFINE, EW, WCH, BF>;
     static bool attr_done = false;
     if (!attr_done) {
         SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
@@ -801,7 +844,7 @@ int launch_tcx_w(const TcArgs& a0, cudaStream_t st) {
     a.tiles_y = (a.H + R - 1) / R;
     a.num_tiles = a.B * a.tiles_x * a.tiles_y;
     CUtensorMap tmap;
-    SIFNN_REQUIRE(encode_planes_map(&tmap, a.in, a.W, a.H, (long long)a.B * a.K, 128, R + 2, TC_KC),
+    SIFNN_REQUIRE(encode_planes_map(&tmap, a.in, a.W, a.H, (long long)a.B * a.K, 128, R + 2, SM::KC),
                   "conv3x3_tc: cuTensorMapEncodeTiled is unavailable or failed");
     const int groups = a.num_tiles / a.tiles_x;
     const int grid = groups < sifnn::num_sms() ? groups : sifnn::num_sms();
@@ -809,12 +852,24 @@ int launch_tcx_w(const TcArgs& a0, cudaStream_t st) {
     return sifnn::check_launch("conv3x3_tcx_kernel");
 }
 
+// SIFNN_TC_BF16=1: 3-term BF16 split in the kx-folded kernel for 16-output-channel layers (experiment; accuracy ~1e-5 instead of ~1e-6)
+bool tc_bf16() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SIFNN_TC_BF16"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+bool tc_use_bf16(int K, int O, int W);
+
 // resident weights when the layer has 2 or 4 chunks of input channels (16 / 32: every 16-output-channel use in ModelB)
 template <int N, int R, int PAD, bool AFFINE, int EW>
 int launch_tcx(const TcArgs& a, cudaStream_t st) {
-    if (N == 16 && a.K == 16) return launch_tcx_w<N, R, PAD, AFFINE, EW, (N == 16 ? 2 : 0)>(a, st);
-    if (N == 16 && a.K == 32) return launch_tcx_w<N, R, PAD, AFFINE, EW, (N == 16 ? 4 : 0)>(a, st);
-    return launch_tcx_w<N, R, PAD, AFFINE, EW, 0>(a, st);
+    if (N == 16 && tc_bf16()) {   // opt-in 3-term BF16 split (16-output-channel layers only so far)
+        if (a.K == 16) return launch_tcx_w<N, R, PAD, AFFINE, EW, (N == 16 ? 1 : 0), (N == 16)>(a, st);
+        if (a.K == 32) return launch_tcx_w<N, R, PAD, AFFINE, EW, (N == 16 ? 2 : 0), (N == 16)>(a, st);
+    }
+    if (N == 16 && a.K == 16) return launch_tcx_w<N, R, PAD, AFFINE, EW, (N == 16 ? 2 : 0), false>(a, st);
+    if (N == 16 && a.K == 32) return launch_tcx_w<N, R, PAD, AFFINE, EW, (N == 16 ? 4 : 0), false>(a, st);
+    return launch_tcx_w<N, R, PAD, AFFINE, EW, 0, false>(a, st);
 }
 
 // the kx-folded kernel serves the 128-pixel MMAs with <= 32 output channels; SIFNN_TC_KXFOLD=0 falls back to the 9-tap kernel (A/B runs)
@@ -831,6 +886,7 @@ bool tc_epi16() {
     if (v < 0) { const char* e = getenv("SIFNN_TC_EPI16"); v = (e && e[0] == '1') ? 1 : 0; }
     return v == 1;
 }
+bool tc_use_bf16(int K, int O, int W) { return tc_bf16() && tc_fold_enabled() && (W % 128 == 0) && O == 16 && (K == 16 || K == 32); }
 bool tc_use_fold(int K, int O, int W) { return tc_fold_enabled() && (W % 128 == 0) && (O == 16 || (O == 32 && K >= 64)); }
 
 template <int N, int R, int MM, int PAD, bool AFFINE>
@@ -906,7 +962,8 @@ extern "C" int sifnn_conv3x3_fwd_tc(const float* in, const float* in_scale, cons
     SIFNN_REQUIRE(sifnn_conv3x3_tc_supported(Cin, Cout, H, W) && B > 0 && B <= 65535, "conv3x3_fwd_tc: unsupported shape Cin=%d Cout=%d H=%d W=%d", Cin, Cout, H, W);
     cudaStream_t st = sifnn::as_stream(stream);
     const int total = (Cin / 8) * 9 * 2 * 2 * Cout * 4;
-    tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, static_cast<float*>(wprep), Cin, Cout, Cin * 9, 9, 0, tc_use_fold(Cin, Cout, W) ? 1 : 0);
+    if (tc_use_bf16(Cin, Cout, W)) tc_prep_weights_bf16_kernel<<<(total / 2 + 255) / 256, 256, 0, st>>>(w, static_cast<unsigned short*>(wprep), Cin, Cout, Cin * 9, 9, 0);
+    else tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, static_cast<float*>(wprep), Cin, Cout, Cin * 9, 9, 0, tc_use_fold(Cin, Cout, W) ? 1 : 0);
     SIFNN_TRY(sifnn::check_launch("tc_prep_weights_kernel"));
     TcArgs a{};
     a.in = in; a.in_scale = in_scale; a.in_shift = in_shift; a.wprep = static_cast<const float*>(wprep); a.bias = bias; a.out = out; a.stats = stats;
@@ -921,7 +978,8 @@ extern "C" int sifnn_conv3x3_dgrad_tc_main(const float* dy, const float* w, floa
     SIFNN_REQUIRE(sifnn_conv3x3_tc_supported(Cout, Cin, H, W) && B > 0 && B <= 65535, "conv3x3_dgrad_tc: unsupported shape");
     cudaStream_t st = sifnn::as_stream(stream);
     const int total = (Cout / 8) * 9 * 2 * 2 * Cin * 4;
-    tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, static_cast<float*>(wprep), Cout, Cin, 9, Cin * 9, 1, tc_use_fold(Cout, Cin, W) ? 1 : 0);
+    if (tc_use_bf16(Cout, Cin, W)) tc_prep_weights_bf16_kernel<<<(total / 2 + 255) / 256, 256, 0, st>>>(w, static_cast<unsigned short*>(wprep), Cout, Cin, 9, Cin * 9, 1);
+    else tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, static_cast<float*>(wprep), Cout, Cin, 9, Cin * 9, 1, tc_use_fold(Cout, Cin, W) ? 1 : 0);
     SIFNN_TRY(sifnn::check_launch("tc_prep_weights_kernel"));
     TcArgs a{};
     a.in = dy; a.wprep = static_cast<const float*>(wprep); a.out = dx;

@@ -106,3 +106,29 @@ def test_tc_wgrad_same_sign_sum_is_unbiased():
     dw = ops.conv3x3_wgrad_tc(x.cuda(), dy.cuda())
     ref = ops.conv3x3_wgrad(x.cuda(), dy.cuda())
     assert rel_err(dw, ref) < 1e-4 / 2
+
+
+def test_tc_bf16x3_optin_mode_accuracy():
+    """Opt-in 3-term BF16 split of the kx-folded kernel (SIFNN_TC_BF16=1, separate process): K = 16 per MMA, stated tolerance 2e-5 per layer
+    (measured 5e-6) against 2e-5 / measured 4e-7 for the default TF32 split."""
+    import os, subprocess, sys
+    code = (
+        "import sys, torch, torch.nn.functional as F\n"
+        "sys.path.insert(0, %r)\n"
+        "import sifnn_b200\n"
+        "from sifnn_b200 import ops\n"
+        "g = torch.Generator().manual_seed(3)\n"
+        "for ci, co, hw in [(16, 16, 128), (32, 16, 256)]:\n"
+        "    x = torch.randn(2, ci, 12, hw, generator=g); w = torch.randn(co, ci, 3, 3, generator=g) * 0.2; dy = torch.randn(2, co, 12, hw, generator=g)\n"
+        "    ref = F.conv2d(F.pad(x.double(), (1, 1, 1, 1), mode='replicate'), w.double())\n"
+        "    y = ops.conv3x3_fwd_tc(x.cuda(), w.cuda()).cpu().double()\n"
+        "    e = float((y - ref).abs().max() / ref.abs().max())\n"
+        "    xx = torch.zeros_like(x, dtype=torch.float64, requires_grad=True)\n"
+        "    (F.conv2d(F.pad(xx, (1, 1, 1, 1), mode='replicate'), w.double()) * dy.double()).sum().backward()\n"
+        "    dx = ops.conv3x3_dgrad_tc(dy.cuda(), w.cuda()).cpu().double()\n"
+        "    e2 = float((dx - xx.grad).abs().max() / xx.grad.abs().max())\n"
+        "    assert 1e-7 < e < 2e-5 and e2 < 2e-5, (ci, co, hw, e, e2)\n"
+        "print('ok')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, SIFNN_TC_BF16="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr
