@@ -91,6 +91,14 @@ int sifnn_conv3x3_wgrad_tc(const float* in, const float* in_scale, const float* 
                            const float* dy, float* dw, void* workspace,
                            int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
 
+/* Train-time quality metrics on the device (utils.py:548-578 psnr_skimage / ssim_skimage, called every step at
+ * train_model_B_gradFTM.py:126-127 after two device->host copies): out2[0] = mean PSNR, out2[1] = mean SSIM
+ * (skimage defaults: 7x7 uniform window, sample covariance, K1 .01, K2 .03) of pred against target, both (B,1,H,W),
+ * data_range = max - min of the whole target batch.  workspace: sifnn_quality_workspace_bytes(B). */
+size_t sifnn_quality_workspace_bytes(int B);
+int sifnn_quality_psnr_ssim(const float* pred, const float* target, float* out2, void* workspace,
+                            int B, int H, int W, sifnn_stream_t stream);
+
 /* nn.BatchNorm2d training statistics -> affine (model.py:136,139,508).
  * stats (2*C doubles: sum, sumsq over n = B*H*W).  Writes scale = gamma*invstd,
  * shift = beta - mean*scale, save_mean, save_invstd (each C floats) and, if

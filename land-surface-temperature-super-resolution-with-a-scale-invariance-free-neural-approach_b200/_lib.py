@@ -14,7 +14,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsifnn_b200.so")
-SOURCES = ["core.cu", "conv3x3.cu", "conv3x3_tc.cu", "wgrad.cu", "wgrad_tc.cu", "elementwise.cu", "loss.cu", "adam.cu", "modelb.cu"]
+SOURCES = ["core.cu", "conv3x3.cu", "conv3x3_tc.cu", "wgrad.cu", "wgrad_tc.cu", "elementwise.cu", "loss.cu", "quality.cu", "adam.cu", "modelb.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared"]
 
@@ -90,6 +90,8 @@ SIGNATURES = {
     "sifnn_tile_gather": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_float] * 4 + [c_void_p]),
     "sifnn_tile_scatter": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float] * 2 + [c_void_p]),
     "sifnn_loss_fwd_bwd": (c_int, [c_int] + [c_void_p] * 7 + [c_float, c_float] + [c_void_p] * 2 + [c_int] * 3 + [c_void_p]),
+    "sifnn_quality_workspace_bytes": (c_size_t, [c_int]),
+    "sifnn_quality_psnr_ssim": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "sifnn_adam_step": (c_int, [c_void_p] * 5 + [c_double] * 4 + [c_float, c_int64, c_void_p]),
     "sifnn_fp32_peak_kernel": (c_int, [c_void_p, c_int, _d, c_void_p]),
     "sifnn_set_tensor_cores": (None, [c_int]),

@@ -11,8 +11,10 @@ reference's own ``load_model`` / ``read_losses`` / ``predict.py`` read them.
 
 Differences, all deliberate: the three loss scalars are accumulated on the device and read
 back once per epoch instead of three ``.item()`` calls per batch; the PSNR / SSIM columns of
-the metrics dict (skimage on the host in the reference, row N2) are filled by an optional
-callable and stay empty otherwise.
+the metrics dict (skimage on the host in the reference, after two device->host copies per
+batch) come from ``quality``: ``"device"`` = the fused CUDA kernel of row N2
+(``ops.psnr_ssim``, accumulated on the device as well), a callable ``(sr, lst_up) -> (psnr,
+ssim)``, or ``None`` (columns stay NaN).
 """
 from __future__ import annotations
 
@@ -24,6 +26,7 @@ from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 import torch
 
 from .trainer import Trainer
+from . import ops
 
 Batch = Tuple[torch.Tensor, torch.Tensor, torch.Tensor]   # (lst, lst_up, ndvi) as ModisDatasetB.__getitem__ collates them
 
@@ -70,57 +73,66 @@ class model_checkpoint:
             self.train_state = "continue"
 
 
+def _quality_fn(quality):
+    """None | "device" | callable(sr, lst_up) -> (psnr, ssim) (floats or a 2-element tensor)."""
+    if quality is None:
+        return None
+    if quality == "device":
+        return lambda sr, lst_up: ops.psnr_ssim(sr.detach().contiguous(), lst_up.contiguous())   # utils.py:548-578 argument order: (predictions, targets)
+    return quality
+
+
 def _epoch_mean(sums: torch.Tensor, n_batches: int) -> Tuple[float, float, float]:
     ds, pl, loss = (sums / max(n_batches, 1)).cpu().tolist()   # the single device -> host read of the epoch
     return ds, pl, loss
 
 
 def train_epoch(trainer: Trainer, batches: Iterable[Batch], device=None,
-                quality: Optional[Callable[[torch.Tensor, torch.Tensor], Tuple[float, float]]] = None):
+                quality=None):
     """``train_step`` of the reference: one pass over the loader in train mode; returns the epoch means
     (ds_loss, percep_loss, loss, psnr, ssim) -- psnr / ssim are NaN without a ``quality`` callable."""
     m = trainer.model
     m.train()
     dev = device or next(m.parameters()).device
     sums = torch.zeros(3, dtype=torch.float64, device=dev)
-    n, q = 0, [0.0, 0.0]
+    qf = _quality_fn(quality)
+    qsum = torch.zeros(2, dtype=torch.float64, device=dev)
+    n = 0
     for lst, lst_up, ndvi in batches:
         lst, lst_up, ndvi = lst.to(dev, non_blocking=True), lst_up.to(dev, non_blocking=True), ndvi.to(dev, non_blocking=True)
         losses, y = trainer._step_impl(lst, ndvi, lst_up)
         sums += losses
-        if quality is not None:
-            p, s = quality(y, lst_up)
-            q[0] += p
-            q[1] += s
+        if qf is not None:
+            qsum += torch.as_tensor(qf(y, lst_up), dtype=torch.float64, device=dev)
         n += 1
     ds, pl, loss = _epoch_mean(sums, n)
-    nan = float("nan")
-    return ds, pl, loss, (q[0] / n if quality and n else nan), (q[1] / n if quality and n else nan)
+    psnr, ssim = ((qsum / max(n, 1)).cpu().tolist() if qf is not None else (float("nan"), float("nan")))
+    return ds, pl, loss, psnr, ssim
 
 
 @torch.no_grad()
 def eval_epoch(trainer: Trainer, batches: Iterable[Batch], device=None,
-               quality: Optional[Callable[[torch.Tensor, torch.Tensor], Tuple[float, float]]] = None):
+               quality=None):
     """``test_step`` of the reference: eval-mode forward + the same losses, no update."""
     m = trainer.model
     dev = device or next(m.parameters()).device
     sums = torch.zeros(3, dtype=torch.float64, device=dev)
-    n, q = 0, [0.0, 0.0]
+    qf = _quality_fn(quality)
+    qsum = torch.zeros(2, dtype=torch.float64, device=dev)
+    n = 0
     for lst, lst_up, ndvi in batches:
         lst, lst_up, ndvi = lst.to(dev, non_blocking=True), lst_up.to(dev, non_blocking=True), ndvi.to(dev, non_blocking=True)
         sums += trainer.evaluate(lst, ndvi, lst_up)
-        if quality is not None:
+        if qf is not None:
             was = m.training
             m.eval()
             y = m(torch.cat((lst_up, ndvi), dim=1))
             m.train(was)
-            p, s = quality(y, lst_up)
-            q[0] += p
-            q[1] += s
+            qsum += torch.as_tensor(qf(y, lst_up), dtype=torch.float64, device=dev)
         n += 1
     ds, pl, loss = _epoch_mean(sums, n)
-    nan = float("nan")
-    return ds, pl, loss, (q[0] / n if quality and n else nan), (q[1] / n if quality and n else nan)
+    psnr, ssim = ((qsum / max(n, 1)).cpu().tolist() if qf is not None else (float("nan"), float("nan")))
+    return ds, pl, loss, psnr, ssim
 
 
 def fit(trainer: Trainer, train_batches: Callable[[], Iterable[Batch]], val_batches: Callable[[], Iterable[Batch]], n_epochs: int,

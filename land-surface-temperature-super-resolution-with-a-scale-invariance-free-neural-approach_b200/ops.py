@@ -204,3 +204,16 @@ def fp32_peak_tflops(iters: int = 4000, reps: int = 5) -> float:
         e1.synchronize()
         best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     return best
+
+
+def psnr_ssim(pred, target):
+    """Mean PSNR and SSIM of a batch (B,1,H,W) on the device, as ``us.psnr_skimage`` / ``us.ssim_skimage`` (utils.py:548-578) compute
+    them on the host.  Returns a (2,) float32 device tensor (psnr, ssim) without synchronising."""
+    _chk(pred, target)
+    if pred.shape != target.shape or pred.dim() != 4 or pred.shape[1] != 1:
+        raise _lib.SifnnError("psnr_ssim: pred and target must both be (B,1,H,W)")
+    B, _, H, W = pred.shape
+    ws = torch.empty(_lib.load().sifnn_quality_workspace_bytes(B), dtype=torch.uint8, device=pred.device)
+    out = torch.empty(2, dtype=torch.float32, device=pred.device)
+    _lib.call("sifnn_quality_psnr_ssim", _p(pred), _p(target), _p(out), _p(ws), B, H, W, _s())
+    return out

@@ -17,7 +17,7 @@ def test_fit_two_epochs_matches_oracle(tmp_path):
     m = model_mod.ModelB_2(in_channels=2).cuda()
     m.load_state_dict(sd)
     tr = sifnn_b200.Trainer(m, "sr2", 0.5, -0.25, 1e-4)   # the SR2 checkpoint's own learning rate
-    model, metrics = sifnn_b200.fit(tr, lambda: tb, lambda: vb, n_epochs=2)
+    model, metrics = sifnn_b200.fit(tr, lambda: tb, lambda: vb, n_epochs=2, quality="device")
     ref = O.Trainer(sd, "sr2", 0.5, -0.25, 1e-4)
     for ep in range(2):
         acc = np.zeros(3)
@@ -35,6 +35,7 @@ def test_fit_two_epochs_matches_oracle(tmp_path):
         got = np.array([metrics["val_dsloss"][ep], metrics["val_perceploss"][ep], metrics["val_loss"][ep]])
         assert np.allclose(got, want, rtol=1e-3), (ep, got, want)
     assert metrics["best_epoch"] == 2 or "best_epoch" in metrics
+    assert all(np.isfinite(v) and 0 < v for v in metrics["train_psnr"] + metrics["val_psnr"]) and all(-1 <= v <= 1 for v in metrics["train_ssim"] + metrics["val_ssim"])
     sd_file, md_file = sifnn_b200.save_model(model, str(tmp_path), "modelB")
     back = torch.load(sd_file, map_location="cpu")
     assert len(back) == 104 and all(not v.is_cuda for v in back.values())
