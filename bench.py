@@ -335,8 +335,10 @@ def run_ours(args):
         traffic = None
         try:  # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
             import csv
-            name = {"wgrad_tc_kernel": "r1k_ncu_full_wgrad_tc_32x16x256_summary.csv",
-                    "wgrad_kernel (SIMT)": "r1i_ncu_full_wgrad_16x16x256_summary.csv"}.get(top["kernel"], "r1j_ncu_full_conv3x3_tc_64x32x128_summary.csv")
+            name = {"wgrad_tc_kernel": "r1l_ncu_full_wgrad_tc_32x16x256_summary.csv",
+                    "wgrad_kernel (SIMT)": "r1i_ncu_full_wgrad_16x16x256_summary.csv",
+                    "conv3x3_tc_kernel (dgrad)": "r1q_ncu_full_conv3x3_tcx_dgrad_16x16x256_summary.csv",
+                    "conv3x3_tc_kernel (fwd)": "r1q_ncu_full_conv3x3_tcx_fwd_32x16x256_summary.csv"}.get(top["kernel"], "r1j_ncu_full_conv3x3_tc_64x32x128_summary.csv")
             vals = {r[0]: r[1] for r in csv.reader(open(os.path.join(ROOT, "profiles", name))) if len(r) >= 2}
             traffic = {"bytes_per_launch": (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e6,
                        "launch": name.replace("_summary.csv", ""), "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum"}
