@@ -146,6 +146,8 @@ def run_reference(args):
 
 
 def workload_name(mode, batch):
+    if mode == "tile":
+        return f"ModelB whole-tile inference: LST 1200x1200 + NDVI 4800x4800 -> 4800x4800, 324 windows in batches of {batch}, block-partitioned over the ranks, fp32"
     if mode == "infer":
         return f"ModelB eval forward, batch {batch} synthetic 64x64 LST + 256x256 NDVI -> 256x256, fp32"
     return f"ModelB SIF-NN-{HYPER[mode][0].upper()} training step, batch {batch}/GPU synthetic patches (64->256), fp32"
@@ -244,7 +246,34 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    if mode == "infer":
+    if mode == "tile":
+        # BASELINE.json configs[4]: one MODIS tile (LST 1200x1200 K, NDVI 4800x4800) -> 4800x4800, 324 windows of 64x64 block-partitioned over
+        # the ranks (predict.py:81-103); every rank holds the tile and writes its own windows, no collective
+        m.eval()
+        stats = dict(mean_lst=307.24, std_lst=5.57, mean_ndvi=0.645, std_ndvi=0.168)
+        g = torch.Generator().manual_seed(4321)
+        tiles_h = [((300 + 8 * torch.rand(1200, 1200, generator=g)).pin_memory(), (0.6 + 0.3 * torch.randn(4800, 4800, generator=g)).pin_memory())
+                   for _ in range(2)]
+        tiles_d = [(l.to(dev), n.to(dev)) for l, n in tiles_h]
+        out_d = torch.zeros(4800, 4800, dtype=torch.float32, device=dev)
+        out_h = torch.empty(4800, 4800, dtype=torch.float32).pin_memory()
+        nwin = 324
+        unit, per_step, metric = "Mpix/s", nwin * PATCH_MPIX, "ModelB whole-tile inference Mpix/s"
+
+        def step(i):
+            l, n = tiles_d[i % 2]
+            return sifnn_b200.super_resolve_tile(m, l, n, stats, batch=B, rank=rank, world_size=world, out=out_d)
+
+        def step_host(i):
+            l, n = tiles_h[i % 2]
+            o = sifnn_b200.super_resolve_tile(m, l.to(dev, non_blocking=True), n.to(dev, non_blocking=True), stats, batch=B, rank=rank,
+                                              world_size=world, out=out_d)
+            out_h.copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out_h
+        h2d, d2h = (1200 * 1200 + 4800 * 4800) * 4, 4800 * 4800 * 4
+        flop_per_step = FWD_GFLOP * 1e9 * nwin / n_gpus
+    elif mode == "infer":
         m.eval()
         unit, per_step, metric = "Mpix/s", B * PATCH_MPIX * n_gpus, "ModelB inference Mpix/s"
 
@@ -299,7 +328,7 @@ def run_ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
     launches = lib.sifnn_launch_count() - launches0
-    if mode != "infer" and getattr(tr, "_graph", None) is not None:
+    if mode.startswith("train") and getattr(tr, "_graph", None) is not None:
         launches = tr.graph_launches * args.steps  # graph replay: the library's counter only saw the capture
     # end-to-end: pinned host buffers in, result scalars (or the SR image) out, every step
     for i in range(2):
@@ -320,11 +349,12 @@ def run_ours(args):
         hbm, bf16, how = peaks()
         value = per_step * args.steps / (ms * 1e-3)
         out = {"metric": metric, "value": value, "unit": unit, "n_gpus": n_gpus, "steps": args.steps, "warmup": n_warm,
-               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if mode == "tile" else "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
                "config": {"workload": workload_name(mode, B), "batch_per_gpu": B, "global_batch": B * n_gpus,
                           "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single", "batchnorm": "local (per-rank statistics)",
-                          "weights": "random init, seed 0", "launch": "cuda-graph replay" if (mode != "infer" and not args.no_graph) else "eager", "l2": f"{nb} distinct input batches rotated + {2.7 * B / 32:.1f} GB of activations per step (> 126 MB L2)"},
+                          "weights": "random init, seed 0", "launch": "cuda-graph replay" if (mode.startswith("train") and not args.no_graph) else "eager", "l2": ("two 98 MB tiles alternated + 1.4 GB of activations per batch of windows (> 126 MB L2)" if mode == "tile" else
+                                 f"{nb} distinct input batches rotated + {(2.7 if mode.startswith('train') else 1.4) * B / 32:.1f} GB of activations per step (> 126 MB L2)")},
                "e2e": {"value": per_step * args.steps / (e2e_ms * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": int(launches), "clocks": clk.summary(),
                "achieved_tflops": flop_per_step * n_gpus * args.steps / (ms * 1e-3) / 1e12}
@@ -333,7 +363,7 @@ def run_ours(args):
         fp32_peak = ops.fp32_peak_tflops()
         tensor_eff = bf16 / 2.0 / 3.0  # TF32 dense = half the measured bf16 peak; fp32 parity costs 3 TF32 products per MAC
         per_kernel = kernel_rooflines(B, fp32_peak, tensor_eff)
-        if mode == "infer":
+        if mode in ("infer", "tile"):
             per_kernel = [k for k in per_kernel if "fwd" in k["kernel"]]
         top = max(per_kernel, key=lambda r: r["ms_per_step"])
         traffic = None
@@ -358,7 +388,7 @@ def run_ours(args):
         import sifnn_oracle as O
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        if mode == "infer":
+        if mode in ("infer", "tile"):
             sd = O.init_state_dict(0)
             x = torch.randn(1, 2, 256, 256)
             with torch.inference_mode():
@@ -394,7 +424,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="train_sr1", choices=["train_sr1", "train_sr2", "infer"])
+    ap.add_argument("--mode", default="train_sr1", choices=["train_sr1", "train_sr2", "infer", "tile"])
     ap.add_argument("--batch", type=int, default=32, help="patches per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=8, help="patches per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--no-graph", action="store_true", help="launch the training step eagerly instead of replaying CUDA graphs")
