@@ -12,6 +12,17 @@ int check_launch(const char* what);
 int num_sms();
 unsigned long long launches();
 
+// Tensor-core convolution with the weight split done beforehand (csrc/conv3x3_tc.cu).  The split weights depend only on the layer, so the
+// network plan prepares ALL layers of a pass in one launch (tc_prep_many) instead of one tiny launch in front of every convolution.
+struct TcPrepJob { const float* w; void* wprep; int K, N, w_so, w_sk, flip, layout, total; };   // layout: 0 nine taps, 1 kx-folded, 2 kx-folded BF16
+TcPrepJob tc_prep_job_fwd(const float* w, void* wprep, int Cin, int Cout, int W);
+TcPrepJob tc_prep_job_dgrad(const float* w, void* wprep, int Cin, int Cout, int W);
+int tc_prep_many(const TcPrepJob* jobs, int n, cudaStream_t st);
+int conv3x3_fwd_tc_prepped(const float* in, const float* in_scale, const float* in_shift, const void* wprep, const float* bias, float* out, double* stats,
+                           int B, int Cin, int Cout, int H, int W, cudaStream_t st);
+int conv3x3_dgrad_tc_main_prepped(const float* dy, const void* wprep, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
+int conv3x3_dgrad_border_cols(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
+
 inline cudaStream_t as_stream(sifnn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -666,6 +666,12 @@ extern "C" int sifnn_conv3x3_dgrad_border(const float* dy, const float* w, float
     return launch_border(dy, w, dx, B, Cin, Cout, H, W, 1, st);
 }
 
+namespace sifnn {
+int conv3x3_dgrad_border_cols(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H, int W, cudaStream_t st) {
+    return launch_border(dy, w, dx, B, Cin, Cout, H, W, 2, st);
+}
+}  // namespace sifnn
+
 extern "C" int sifnn_conv3x3_dgrad_tc(const float* dy, const float* w, float* dx, int accumulate, void* wprep, int B, int Cin, int Cout,
                                       int H, int W, sifnn_stream_t stream) {
     // the tensor-core kernel folds the top/bottom row terms in as extra tap MMAs; only the column terms (+ corners) are left

@@ -774,57 +774,10 @@ __global__ void __launch_bounds__((EW + 2 + (EW == 16 ? 4 : 8)) * 32, 1) conv3x3
     }
 }
 
-// Split the weights of one layer into TF32 hi / lo parts in the exact shared-memory image of a stage.
-// fold = 0: wprep[chunk][tap][q][row][e], row < N: hi of W[n = row][c = 8*chunk + 4q + e][tap], row >= N: lo of W[n = row - N].
-// fold = 1: wprep[chunk][ky][q][row][e], row = (s * 3 + kx) * N + n  (hi rows of the three kx first, then the lo rows).
-__global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wprep, int K, int N, int w_so, int w_sk, int flip, int fold) {
-    const int total = (K / 8) * 9 * 2 * 2 * N * 4;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int e = idx & 3;
-        int n, q, t, chunk, lo;
-        if (!fold) {
-            const int row = (idx >> 2) % (2 * N);
-            q = ((idx >> 2) / (2 * N)) & 1;
-            t = ((idx >> 2) / (2 * N * 2)) % 9;
-            chunk = (idx >> 2) / (2 * N * 2 * 9);
-            n = row < N ? row : row - N;
-            lo = row >= N;
-        } else {
-            const int row = (idx >> 2) % (6 * N);
-            q = ((idx >> 2) / (6 * N)) & 1;
-            const int ky = ((idx >> 2) / (6 * N * 2)) % 3;
-            chunk = (idx >> 2) / (6 * N * 2 * 3);
-            lo = row >= 3 * N;
-            const int rr = lo ? row - 3 * N : row;
-            t = ky * 3 + rr / N;
-            n = rr % N;
-        }
-        const int c = chunk * 8 + 4 * q + e;
-        const float v = __ldg(w + (size_t)n * w_so + (size_t)c * w_sk + (flip ? 8 - t : t));
-        const float hi = tf32_hi(v);
-        wprep[idx] = lo ? v - hi : hi;
-    }
-}
-
-// BF16 variant of the fold layout: wprep[chunk of 16 ch][ky][q][row][8 bf16], row = (s * 3 + kx) * N + n, channel = 16*chunk + 8q + e
-__global__ void tc_prep_weights_bf16_kernel(const float* __restrict__ w, unsigned short* __restrict__ wprep, int K, int N, int w_so, int w_sk, int flip) {
-    const int total = (K / 16) * 3 * 2 * 6 * N * 8;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int e = idx & 7;
-        const int row = (idx >> 3) % (6 * N);
-        const int q = ((idx >> 3) / (6 * N)) & 1;
-        const int ky = ((idx >> 3) / (6 * N * 2)) % 3;
-        const int chunk = (idx >> 3) / (6 * N * 2 * 3);
-        const int lo = row >= 3 * N;
-        const int rr = lo ? row - 3 * N : row;
-        const int t = ky * 3 + rr / N, n = rr % N;
-        const int c = chunk * 16 + 8 * q + e;
-        const float v = __ldg(w + (size_t)n * w_so + (size_t)c * w_sk + (flip ? 8 - t : t));
-        unsigned short h, l;
-        bf16_split(v, h, l);
-        wprep[idx] = lo ? l : h;
-    }
-}
+// Weight split layouts (produced by tc_prep_many_kernel at the end of this file), the exact shared-memory image of a stage:
+// layout 0: wprep[chunk][tap][q][row][e], row < N: hi of W[n = row][c = 8*chunk + 4q + e][tap], row >= N: lo of W[n = row - N];
+// layout 1: wprep[chunk][ky][q][row][e], row = (s * 3 + kx) * N + n  (hi rows of the three kx first, then the lo rows);
+// layout 2: the same with BF16 pairs, wprep[chunk of 16 ch][ky][q][row][8 bf16], channel = 16*chunk + 8q + e.
 
 template <int N, int R, int PAD, bool AFFINE, int EW, int WCH, bool BF>
 int launch_tcx_w(const TcArgs& a0, cudaStream_t st) {
@@ -954,6 +907,103 @@ extern "C" int sifnn_conv3x3_tc_supported(int Cin, int Cout, int H, int W) {
 
 extern "C" size_t sifnn_conv3x3_tc_wprep_bytes(int Cin, int Cout) { return (size_t)(Cin / 8) * 9 * 2 * 2 * Cout * 4 * sizeof(float); }
 
+namespace {
+
+constexpr int TC_PREP_MAX = 24;
+struct TcPrepBatch { sifnn::TcPrepJob j[TC_PREP_MAX]; };
+
+// every job of the batch in one launch: blockIdx.y = job, the x dimension strides over that job's elements
+__global__ void __launch_bounds__(256) tc_prep_many_kernel(const __grid_constant__ TcPrepBatch batch) {
+    const sifnn::TcPrepJob& J = batch.j[blockIdx.y];
+    const int N = J.N;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < J.total; idx += gridDim.x * blockDim.x) {
+        int n, q, t, c, lo;
+        if (J.layout == 0) {
+            const int e = idx & 3, row = (idx >> 2) % (2 * N);
+            q = ((idx >> 2) / (2 * N)) & 1;
+            t = ((idx >> 2) / (2 * N * 2)) % 9;
+            const int chunk = (idx >> 2) / (2 * N * 2 * 9);
+            n = row < N ? row : row - N;
+            lo = row >= N;
+            c = chunk * 8 + 4 * q + e;
+        } else if (J.layout == 1) {
+            const int e = idx & 3, row = (idx >> 2) % (6 * N);
+            q = ((idx >> 2) / (6 * N)) & 1;
+            const int ky = ((idx >> 2) / (6 * N * 2)) % 3, chunk = (idx >> 2) / (6 * N * 2 * 3);
+            lo = row >= 3 * N;
+            const int rr = lo ? row - 3 * N : row;
+            t = ky * 3 + rr / N;
+            n = rr % N;
+            c = chunk * 8 + 4 * q + e;
+        } else {
+            const int e = idx & 7, row = (idx >> 3) % (6 * N);
+            q = ((idx >> 3) / (6 * N)) & 1;
+            const int ky = ((idx >> 3) / (6 * N * 2)) % 3, chunk = (idx >> 3) / (6 * N * 2 * 3);
+            lo = row >= 3 * N;
+            const int rr = lo ? row - 3 * N : row;
+            t = ky * 3 + rr / N;
+            n = rr % N;
+            c = chunk * 16 + 8 * q + e;
+        }
+        const float v = __ldg(J.w + (size_t)n * J.w_so + (size_t)c * J.w_sk + (J.flip ? 8 - t : t));
+        if (J.layout == 2) {
+            unsigned short h, l;
+            bf16_split(v, h, l);
+            static_cast<unsigned short*>(J.wprep)[idx] = lo ? l : h;
+        } else {
+            const float hi = tf32_hi(v);
+            static_cast<float*>(J.wprep)[idx] = lo ? v - hi : hi;
+        }
+    }
+}
+
+sifnn::TcPrepJob make_prep_job(const float* w, void* wprep, int K, int N, int w_so, int w_sk, int flip, int W) {
+    sifnn::TcPrepJob j{};
+    j.w = w; j.wprep = wprep; j.K = K; j.N = N; j.w_so = w_so; j.w_sk = w_sk; j.flip = flip;
+    j.layout = tc_use_bf16(K, N, W) ? 2 : (tc_use_fold(K, N, W) ? 1 : 0);
+    j.total = (j.layout == 2) ? (K / 16) * 3 * 2 * 6 * N * 8 : (K / 8) * 9 * 2 * 2 * N * 4;
+    return j;
+}
+
+}  // namespace
+
+namespace sifnn {
+
+TcPrepJob tc_prep_job_fwd(const float* w, void* wprep, int Cin, int Cout, int W) { return make_prep_job(w, wprep, Cin, Cout, Cin * 9, 9, 0, W); }
+TcPrepJob tc_prep_job_dgrad(const float* w, void* wprep, int Cin, int Cout, int W) { return make_prep_job(w, wprep, Cout, Cin, 9, Cin * 9, 1, W); }
+
+int tc_prep_many(const TcPrepJob* jobs, int n, cudaStream_t st) {
+    for (int i0 = 0; i0 < n; i0 += TC_PREP_MAX) {
+        TcPrepBatch b{};
+        const int m = n - i0 < TC_PREP_MAX ? n - i0 : TC_PREP_MAX;
+        int mx = 0;
+        for (int i = 0; i < m; ++i) { b.j[i] = jobs[i0 + i]; if (b.j[i].total > mx) mx = b.j[i].total; }
+        if (m == 0 || mx == 0) continue;
+        int bx = (mx + 256 * 4 - 1) / (256 * 4);
+        if (bx > 64) bx = 64;
+        tc_prep_many_kernel<<<dim3(bx, m), 256, 0, st>>>(b);
+        SIFNN_TRY(check_launch("tc_prep_many_kernel"));
+    }
+    return 0;
+}
+
+int conv3x3_fwd_tc_prepped(const float* in, const float* in_scale, const float* in_shift, const void* wprep, const float* bias, float* out, double* stats,
+                           int B, int Cin, int Cout, int H, int W, cudaStream_t st) {
+    TcArgs a{};
+    a.in = in; a.in_scale = in_scale; a.in_shift = in_shift; a.wprep = static_cast<const float*>(wprep); a.bias = bias; a.out = out; a.stats = stats;
+    a.B = B; a.K = Cin; a.O = Cout; a.H = H; a.W = W; a.accumulate = 0;
+    return in_scale ? dispatch_tc<0, true>(a, st) : dispatch_tc<0, false>(a, st);
+}
+
+int conv3x3_dgrad_tc_main_prepped(const float* dy, const void* wprep, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st) {
+    TcArgs a{};
+    a.in = dy; a.wprep = static_cast<const float*>(wprep); a.out = dx;
+    a.B = B; a.K = Cout; a.O = Cin; a.H = H; a.W = W; a.accumulate = accumulate ? 1 : 0;
+    return dispatch_tc<1, false>(a, st);
+}
+
+}  // namespace sifnn
+
 extern "C" int sifnn_conv3x3_fwd_tc(const float* in, const float* in_scale, const float* in_shift, const float* w, const float* bias,
                                     float* out, double* stats, void* wprep, int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream) {
     SIFNN_REQUIRE(in && w && out && wprep, "conv3x3_fwd_tc: null pointer");
@@ -961,14 +1011,9 @@ extern "C" int sifnn_conv3x3_fwd_tc(const float* in, const float* in_scale, cons
     SIFNN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "conv3x3_fwd_tc: in_scale/in_shift must both be set or both NULL");
     SIFNN_REQUIRE(sifnn_conv3x3_tc_supported(Cin, Cout, H, W) && B > 0 && B <= 65535, "conv3x3_fwd_tc: unsupported shape Cin=%d Cout=%d H=%d W=%d", Cin, Cout, H, W);
     cudaStream_t st = sifnn::as_stream(stream);
-    const int total = (Cin / 8) * 9 * 2 * 2 * Cout * 4;
-    if (tc_use_bf16(Cin, Cout, W)) tc_prep_weights_bf16_kernel<<<(total / 2 + 255) / 256, 256, 0, st>>>(w, static_cast<unsigned short*>(wprep), Cin, Cout, Cin * 9, 9, 0);
-    else tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, static_cast<float*>(wprep), Cin, Cout, Cin * 9, 9, 0, tc_use_fold(Cin, Cout, W) ? 1 : 0);
-    SIFNN_TRY(sifnn::check_launch("tc_prep_weights_kernel"));
-    TcArgs a{};
-    a.in = in; a.in_scale = in_scale; a.in_shift = in_shift; a.wprep = static_cast<const float*>(wprep); a.bias = bias; a.out = out; a.stats = stats;
-    a.B = B; a.K = Cin; a.O = Cout; a.H = H; a.W = W; a.accumulate = 0;
-    return in_scale ? dispatch_tc<0, true>(a, st) : dispatch_tc<0, false>(a, st);
+    const sifnn::TcPrepJob job = sifnn::tc_prep_job_fwd(w, wprep, Cin, Cout, W);
+    SIFNN_TRY(sifnn::tc_prep_many(&job, 1, st));
+    return sifnn::conv3x3_fwd_tc_prepped(in, in_scale, in_shift, wprep, bias, out, stats, B, Cin, Cout, H, W, st);
 }
 
 // Main (zero-padded, transposed) part of the data gradient; the caller adds the replicate-padding border terms.
@@ -977,12 +1022,7 @@ extern "C" int sifnn_conv3x3_dgrad_tc_main(const float* dy, const float* w, floa
     SIFNN_REQUIRE(dy && w && dx && wprep, "conv3x3_dgrad_tc: null pointer");
     SIFNN_REQUIRE(sifnn_conv3x3_tc_supported(Cout, Cin, H, W) && B > 0 && B <= 65535, "conv3x3_dgrad_tc: unsupported shape");
     cudaStream_t st = sifnn::as_stream(stream);
-    const int total = (Cout / 8) * 9 * 2 * 2 * Cin * 4;
-    if (tc_use_bf16(Cout, Cin, W)) tc_prep_weights_bf16_kernel<<<(total / 2 + 255) / 256, 256, 0, st>>>(w, static_cast<unsigned short*>(wprep), Cout, Cin, 9, Cin * 9, 1);
-    else tc_prep_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, static_cast<float*>(wprep), Cout, Cin, 9, Cin * 9, 1, tc_use_fold(Cout, Cin, W) ? 1 : 0);
-    SIFNN_TRY(sifnn::check_launch("tc_prep_weights_kernel"));
-    TcArgs a{};
-    a.in = dy; a.wprep = static_cast<const float*>(wprep); a.out = dx;
-    a.B = B; a.K = Cout; a.O = Cin; a.H = H; a.W = W; a.accumulate = accumulate ? 1 : 0;
-    return dispatch_tc<1, false>(a, st);
+    const sifnn::TcPrepJob job = sifnn::tc_prep_job_dgrad(w, wprep, Cin, Cout, W);
+    SIFNN_TRY(sifnn::tc_prep_many(&job, 1, st));
+    return sifnn::conv3x3_dgrad_tc_main_prepped(dy, wprep, dx, accumulate, B, Cin, Cout, H, W, st);
 }

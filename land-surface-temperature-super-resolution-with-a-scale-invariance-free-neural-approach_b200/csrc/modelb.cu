@@ -96,7 +96,8 @@ struct Workspace {
     float* gR[3];
     float* gU[3];
     void* wgrad_ws;
-    void* wprep;  // hi/lo-split weights of the convolution in flight (tensor-core path)
+    void* wprep_f[SIFNN_MODELB_NCONV];  // hi/lo-split weights per layer, forward layout (tensor-core path; all prepared by ONE launch per pass)
+    void* wprep_d[SIFNN_MODELB_NCONV];  // same, data-gradient layout (training only)
     size_t bytes;
 };
 
@@ -118,17 +119,11 @@ Workspace carve(const Net& n, void* base, int B, int H, int W, int train) {
     w.invstd = c.take<float>(n.bn_total);
     w.stats = c.take<double>(2 * n.bn_total);
     w.bsums = c.take<double>(2 * n.bn_total);
-    {
-        size_t mx = 0;
-        for (int i = 0; i < SIFNN_MODELB_NCONV; ++i) {
-            const size_t b = sifnn_conv3x3_tc_wprep_bytes((n.conv[i].cin + 7) / 8 * 8, n.conv[i].cout);
-            const size_t b2 = sifnn_conv3x3_tc_wprep_bytes((n.conv[i].cout + 7) / 8 * 8, n.conv[i].cin);
-            if (b > mx) mx = b;
-            if (b2 > mx) mx = b2;
-        }
-        w.wprep = c.take<char>(mx);
-    }
+    for (int i = 0; i < SIFNN_MODELB_NCONV; ++i)
+        w.wprep_f[i] = c.take<char>(sifnn_conv3x3_tc_wprep_bytes((n.conv[i].cin + 7) / 8 * 8, n.conv[i].cout));
     if (train) {
+        for (int i = 0; i < SIFNN_MODELB_NCONV; ++i)
+            w.wprep_d[i] = c.take<char>(sifnn_conv3x3_tc_wprep_bytes((n.conv[i].cout + 7) / 8 * 8, n.conv[i].cin));
         for (int i = 0; i < SIFNN_MODELB_NBN; ++i) w.g[i] = c.take<float>((size_t)B * n.conv[i].cout * hw[n.conv[i].level]);
         for (int k = 0; k < 3; ++k) w.gR[k] = c.take<float>((size_t)B * n.d[k] * hw[k + 1]);
         for (int k = 0; k < 3; ++k) w.gU[k] = c.take<float>((size_t)B * n.d[3 - k] * hw[2 - k]);
@@ -216,6 +211,18 @@ extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* pa
         SIFNN_TRY(sifnn::check_launch("bn_eval_affine_all_kernel"));
     }
 
+    // tensor-core layers: split the weights of all of them in one launch
+    auto fwd_tc = [&](int i) {
+        const ConvDesc& c = n.conv[i];
+        return tc_enabled() && c.cout <= 64 && sifnn_conv3x3_tc_supported(c.cin, c.cout, hs[c.level], ws[c.level]) != 0;
+    };
+    {
+        sifnn::TcPrepJob jobs[SIFNN_MODELB_NCONV];
+        int nj = 0;
+        for (int i = 0; i < SIFNN_MODELB_NCONV; ++i)
+            if (fwd_tc(i)) jobs[nj++] = sifnn::tc_prep_job_fwd(params + n.w_off[i], w.wprep_f[i], n.conv[i].cin, n.conv[i].cout, ws[n.conv[i].level]);
+        SIFNN_TRY(sifnn::tc_prep_many(jobs, nj, st));
+    }
     // conv i reading `in` (plain if aff < 0, else BatchNorm+ReLU of layer `aff` applied on load)
     auto conv = [&](int i, const float* in, int aff, float* out) -> int {
         const ConvDesc& c = n.conv[i];
@@ -224,9 +231,9 @@ extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* pa
         const float* isc = aff >= 0 ? w.scale + n.bn_off[aff] : nullptr;
         const float* ish = aff >= 0 ? w.shift + n.bn_off[aff] : nullptr;
         double* st_ptr = (bn && train) ? w.stats + 2 * n.bn_off[i] : nullptr;
-        if (tc_enabled() && c.cout <= 64 && sifnn_conv3x3_tc_supported(c.cin, c.cout, hs[l], ws[l])) {
-            SIFNN_TRY(sifnn_conv3x3_fwd_tc(in, isc, ish, params + n.w_off[i], bn ? nullptr : params + n.bias_off, out, st_ptr, w.wprep, B, c.cin,
-                                           c.cout, hs[l], ws[l], stream));
+        if (fwd_tc(i)) {
+            SIFNN_TRY(sifnn::conv3x3_fwd_tc_prepped(in, isc, ish, w.wprep_f[i], bn ? nullptr : params + n.bias_off, out, st_ptr, B, c.cin, c.cout, hs[l],
+                                                    ws[l], st));
         } else {
             SIFNN_TRY(sifnn_conv3x3_fwd(in, isc, ish, params + n.w_off[i], bn ? nullptr : params + n.bias_off, out, st_ptr, B, c.cin, c.cout, hs[l],
                                         ws[l], stream));
@@ -286,10 +293,25 @@ extern "C" int sifnn_modelb_backward(const sifnn_modelb_cfg* cfg, const float* p
         return sifnn_conv3x3_wgrad(in, aff >= 0 ? sc(aff) : nullptr, aff >= 0 ? sh(aff) : nullptr, g, grads + n.w_off[i],
                                    i == 17 ? grads + n.bias_off : nullptr, w.wgrad_ws, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
     };
+    auto dgrad_tc = [&](int i) {
+        const ConvDesc& c = n.conv[i];
+        return i > 0 && tc_enabled() && sifnn_conv3x3_tc_supported(c.cout, c.cin, hs[c.level], ws[c.level]) != 0;
+    };
+    {   // data-gradient weight splits of the layers this call touches, one launch (decoder = conv 11..17, encoder = conv 1..10)
+        sifnn::TcPrepJob jobs[SIFNN_MODELB_NCONV];
+        int nj = 0;
+        const int lo = (phase == 2) ? 1 : ((phase == 1) ? 11 : 1), hi = (phase == 2) ? 10 : 17;
+        for (int i = lo; i <= hi; ++i)
+            if (dgrad_tc(i)) jobs[nj++] = sifnn::tc_prep_job_dgrad(params + n.w_off[i], w.wprep_d[i], n.conv[i].cin, n.conv[i].cout, ws[n.conv[i].level]);
+        SIFNN_TRY(sifnn::tc_prep_many(jobs, nj, st));
+    }
     auto dgrad = [&](int i, const float* g, float* dx, int accumulate) -> int {
         const ConvDesc& c = n.conv[i];
-        if (tc_enabled() && sifnn_conv3x3_tc_supported(c.cout, c.cin, hs[c.level], ws[c.level]))
-            return sifnn_conv3x3_dgrad_tc(g, params + n.w_off[i], dx, accumulate, w.wprep, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
+        if (dgrad_tc(i)) {
+            // the tensor-core kernel folds the top/bottom row terms of the padding adjoint in as extra tap MMAs; the column terms (+ corners) follow
+            SIFNN_TRY(sifnn::conv3x3_dgrad_tc_main_prepped(g, w.wprep_d[i], dx, accumulate, B, c.cin, c.cout, hs[c.level], ws[c.level], st));
+            return sifnn::conv3x3_dgrad_border_cols(g, params + n.w_off[i], dx, B, c.cin, c.cout, hs[c.level], ws[c.level], st);
+        }
         return sifnn_conv3x3_dgrad(g, params + n.w_off[i], dx, accumulate, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
     };
     // BatchNorm+ReLU backward of layer i: dY (gradient w.r.t. the activated output) -> dx (w.r.t. raw[i])
