@@ -281,15 +281,13 @@ def run_ours(args):
             with torch.inference_mode():
                 return m.forward_from_lowres(*devb[i % nb])
 
-        host_out = torch.empty((B, 1, 256, 256), dtype=torch.float32).pin_memory()   # the caller's result buffer (pinned, like the inputs)
+        host_out = [torch.empty((B, 1, 256, 256), dtype=torch.float32).pin_memory() for _ in range(2)]   # the caller's result buffers (pinned)
+        pipe = sifnn_b200.PipelinedInference(m)   # H2D of step i+1 and D2H of step i-1 overlap the forward of step i; flushed by the barrier below
 
         def step_host(i):
             l, n = host[i % nb]
-            with torch.inference_mode():
-                y = m.forward_from_lowres(l.to(dev, non_blocking=True), n.to(dev, non_blocking=True))
-                host_out.copy_(y, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return host_out
+            pipe.submit(l, n, host_out[i % 2])
+            return host_out[i % 2]
         h2d, d2h = B * (64 * 64 + 256 * 256) * 4, B * 256 * 256 * 4
         flop_per_step = FWD_GFLOP * 1e9 * B
     else:
@@ -331,12 +329,17 @@ def run_ours(args):
     if mode.startswith("train") and getattr(tr, "_graph", None) is not None:
         launches = tr.graph_launches * args.steps  # graph replay: the library's counter only saw the capture
     # end-to-end: pinned host buffers in, result scalars (or the SR image) out, every step
+    def flush_host():
+        if mode == "infer":
+            pipe.flush()   # every result has landed in its pinned host buffer
     for i in range(2):
         step_host(i)
+    flush_host()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         step_host(i)
+    flush_host()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)

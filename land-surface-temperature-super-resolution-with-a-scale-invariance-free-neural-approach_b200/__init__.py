@@ -15,6 +15,7 @@ from .losses import sr_losses, sr1_losses, sr2_losses, loss_fwd_bwd  # noqa: F40
 from .trainer import Trainer  # noqa: F401
 from .parallel import block_partition, shard_batch, BucketedAllReduce  # noqa: F401
 from .tile import super_resolve_tile, window_list  # noqa: F401
+from .serving import PipelinedInference  # noqa: F401
 from .fit import model_checkpoint, fit, train_epoch, eval_epoch, save_model, load_model, save_metrics  # noqa: F401
 
 

@@ -54,3 +54,23 @@ def test_tile_matches_reference_loop_and_shards():
         sifnn_b200.super_resolve_tile(m, lst.cuda(), ndvi.cuda(), STATS, batch=8, rank=r, world_size=3, out=acc)
     assert torch.equal(acc, out)
     assert sifnn_b200.window_list(1200, 1200)[0].numel() == 324
+
+
+def test_pipelined_inference_matches_direct_forward():
+    """Three-stream pipelined serving path (serving.py): same bits as the direct forward, results in the caller's pinned buffers."""
+    sd = load_ckpt("1009")
+    m = model_mod.ModelB_2(2)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(12)
+    batches = [(torch.randn(3, 1, 64, 64, generator=g).pin_memory(), torch.randn(3, 1, 256, 256, generator=g).pin_memory()) for _ in range(5)]
+    outs = [torch.empty(3, 1, 256, 256).pin_memory() for _ in range(5)]
+    pipe = sifnn_b200.PipelinedInference(m)
+    for (l, n), o in zip(batches, outs):
+        pipe.submit(l, n, o)
+    pipe.flush()
+    with torch.inference_mode():
+        for (l, n), o in zip(batches, outs):
+            assert torch.equal(m.forward_from_lowres(l.cuda(), n.cuda()).cpu(), o)
+    with pytest.raises(sifnn_b200.SifnnError):
+        pipe.submit(batches[0][0].clone(), batches[0][1], outs[0])   # not pinned
