@@ -307,7 +307,12 @@ def run_ours(args):
             def step(i):
                 return tr.step(*devb[i % nb])
 
+        losses_host = [torch.zeros(3, dtype=torch.float64).pin_memory() for _ in range(4)]
+
         def step_host(i):
+            if use_graph:   # H2D of step i+1 overlaps step i (copy stream); the three loss scalars come back asynchronously every step
+                tr.step_host_async(*host[i % nb], losses_host[i % 4])
+                return losses_host[i % 4]
             return tr.step_host(*host[i % nb])
         h2d, d2h = B * (64 * 64 + 256 * 256) * 4, 3 * 8
         flop_per_step = STEP_GFLOP * 1e9 * B

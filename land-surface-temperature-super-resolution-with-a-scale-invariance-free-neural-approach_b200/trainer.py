@@ -108,6 +108,39 @@ class Trainer:
         ds, pl, loss = losses.cpu().tolist()
         return ds, pl, loss
 
+    def step_host_async(self, lst_pinned: torch.Tensor, ndvi_pinned: torch.Tensor, losses_pinned: torch.Tensor) -> None:
+        """End-to-end step from pinned HOST buffers without a host synchronisation: the H2D copy of this step's inputs runs on a copy
+        stream (so it overlaps the previous step, which is still executing when the host gets here), the step replays the captured
+        graphs, and the three loss scalars are copied into ``losses_pinned`` ((3,) float64, pinned) asynchronously -- valid after the
+        caller's next stream / device synchronisation.  Needs capture() first."""
+        if self._graph is None:
+            raise SifnnError("call capture() first")
+        for t in (lst_pinned, ndvi_pinned, losses_pinned):
+            if t.is_cuda or not t.is_pinned():
+                raise SifnnError("step_host_async takes pinned host tensors")
+        dev = self._static_lst.device
+        hp = getattr(self, "_host_pipe", None)
+        if hp is None:
+            hp = self._host_pipe = {"stream": torch.cuda.Stream(dev), "n": 0,
+                                    "slots": [{"lst": torch.empty_like(self._static_lst), "ndvi": torch.empty_like(self._static_ndvi),
+                                               "in_done": torch.cuda.Event(), "consumed": torch.cuda.Event(), "used": False} for _ in range(2)]}
+        b = hp["slots"][hp["n"] % 2]
+        cur = torch.cuda.current_stream(dev)
+        if b["used"]:
+            hp["stream"].wait_event(b["consumed"])
+        with torch.cuda.stream(hp["stream"]):
+            b["lst"].copy_(lst_pinned, non_blocking=True)
+            b["ndvi"].copy_(ndvi_pinned, non_blocking=True)
+            b["in_done"].record(hp["stream"])
+        cur.wait_event(b["in_done"])
+        self._static_lst.copy_(b["lst"], non_blocking=True)
+        self._static_ndvi.copy_(b["ndvi"], non_blocking=True)
+        b["consumed"].record(cur)
+        b["used"] = True
+        hp["n"] += 1
+        self._replay_or_run(self._segs, eager=False, fgrad=self._ar[0], dec=self._ar[1])
+        losses_pinned.copy_(self._static_losses, non_blocking=True)
+
     @torch.no_grad()
     def evaluate(self, lst: torch.Tensor, ndvi: torch.Tensor, lst_up: Optional[torch.Tensor] = None) -> torch.Tensor:
         """The reference's ``test_step`` body (train_model_B_gradFTM.py:181-215): eval-mode forward + losses."""

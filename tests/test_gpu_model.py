@@ -285,3 +285,28 @@ def test_graph_replay_matches_eager():
     pa = torch.cat([p.detach().reshape(-1) for p in a.parameters()])
     pb = torch.cat([p.detach().reshape(-1) for p in b.parameters()])
     assert rel_err(pb, pa) < 1e-6
+
+
+def test_step_host_async_matches_graph_step():
+    """Pipelined end-to-end step (copy stream + asynchronous loss read-back) against the plain graph replay on the same batches."""
+    sd = O.init_state_dict(6)
+    g = torch.Generator().manual_seed(6)
+    batches = [(torch.randn(2, 1, 64, 64, generator=g).pin_memory(), torch.randn(2, 1, 256, 256, generator=g).pin_memory()) for _ in range(4)]
+    a, b = make_model(sd=sd).train(), make_model(sd=sd).train()
+    ta, tb = sifnn_b200.Trainer(a, "sr2", 0.5, -0.25, 1e-4), sifnn_b200.Trainer(b, "sr2", 0.5, -0.25, 1e-4)
+    for t, m in ((ta, a), (tb, b)):
+        sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+        t.capture(batches[0][0].cuda(), batches[0][1].cuda())
+        m.load_state_dict(sd0)
+        t._opt["m"].zero_(); t._opt["v"].zero_(); t._opt["t"].zero_()
+    outs = [torch.zeros(3, dtype=torch.float64).pin_memory() for _ in range(4)]
+    ref = []
+    for i, (l, n) in enumerate(batches):
+        ta.step_host_async(l, n, outs[i])
+        ref.append(tb.step_graph(l.cuda(), n.cuda()).clone())
+    torch.cuda.synchronize()
+    for o, r in zip(outs, ref):
+        assert torch.equal(o, r.cpu())
+    pa = torch.cat([p.detach().reshape(-1) for p in a.parameters()])
+    pb = torch.cat([p.detach().reshape(-1) for p in b.parameters()])
+    assert torch.equal(pa, pb)
