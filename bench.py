@@ -275,6 +275,8 @@ def run_ours(args):
         flop_per_step = FWD_GFLOP * 1e9 * nwin / n_gpus
     elif mode == "infer":
         m.eval()
+        if B <= 8:
+            m.enable_eval_graphs(True, max_batch=8)   # small batches (predict.py runs batch 1) are launch-bound: replay a captured graph
         unit, per_step, metric = "Mpix/s", B * PATCH_MPIX * n_gpus, "ModelB inference Mpix/s"
 
         def step(i):

@@ -191,9 +191,11 @@ class ModelB_2(nn.Module):
         self.ub3 = UpBlock(d[1], d[0], bilinear, padding_mode, activation=activation)
         self.outlay = nn.Conv2d(d[0], 1, kernel_size=3, stride=1, padding=1, padding_mode=padding_mode)
 
-    def __getstate__(self):
+    def __getstate__(self):  # (graphs and native state are rebuilt on demand)
         d = self.__dict__.copy()
         d.pop("_sifnn_state", None)  # flat buffers / workspaces are rebuilt lazily
+        d.pop("_eval_graphs", None)  # CUDA graphs are not picklable; re-enable with enable_eval_graphs()
+        d.pop("_eval_graph_max", None)
         return d
 
     # ------------------------------------------------------------------ native state
@@ -351,7 +353,52 @@ class ModelB_2(nn.Module):
     def forward_from_lowres(self, lst, ndvi):
         """Fused input stage: bicubic x4 of the (B,1,h,w) LST patch (cv2.INTER_CUBIC,
         reference utils.py:163-180) + concat with the (B,1,4h,4w) NDVI patch, then forward."""
+        g = getattr(self, "_eval_graphs", None)
+        if g is not None and not self.training and lst.is_cuda and lst.shape[0] <= self._eval_graph_max and not torch.cuda.is_current_stream_capturing():
+            return self._graph_eval(lst, ndvi)
         return self.forward(bicubic4_cat(lst, ndvi))
+
+    # ------------------------------------------------------------------ CUDA-graph replay for small eval batches
+    def enable_eval_graphs(self, on: bool = True, max_batch: int = 8) -> None:
+        """Replay a captured CUDA graph for eval-mode ``forward_from_lowres`` calls with at most ``max_batch`` patches.  The per-window
+        loop of predict.py:84-103 runs batch 1, where the ~35 kernel launches of a forward cost more than the kernels themselves."""
+        object.__setattr__(self, "_eval_graphs", {} if on else None)
+        object.__setattr__(self, "_eval_graph_max", int(max_batch))
+
+    def _graph_eval(self, lst: torch.Tensor, ndvi: torch.Tensor) -> torch.Tensor:
+        if lst.dtype != torch.float32 or ndvi.dtype != torch.float32 or not ndvi.is_cuda:
+            raise SifnnError("forward_from_lowres needs fp32 CUDA tensors")
+        st = self._ensure_flat(lst.device)
+        B, _, h, w = lst.shape
+        key = (B, h, w, lst.device, st["flat"].data_ptr(), st["rm"].data_ptr())
+        ent = self._eval_graphs.get(key)
+        if ent is None:
+            dev = lst.device
+            ent = {"lst": torch.empty_like(lst, memory_format=torch.contiguous_format), "ndvi": torch.empty_like(ndvi, memory_format=torch.contiguous_format),
+                   "x": torch.empty((B, 2, 4 * h, 4 * w), dtype=torch.float32, device=dev),
+                   "y": torch.empty((B, 1, 4 * h, 4 * w), dtype=torch.float32, device=dev)}
+            self._check_input(ent["x"])
+            ent["ws"] = torch.empty(self._workspace_bytes(B, 4 * h, 4 * w, False), dtype=torch.uint8, device=dev)
+
+            def run():
+                bicubic4_cat(ent["lst"], ent["ndvi"], out=ent["x"])
+                self._run_forward(ent["x"], train=False, keep=False, ws=ent["ws"], y=ent["y"])
+            ent["lst"].copy_(lst)
+            ent["ndvi"].copy_(ndvi)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                run()                      # warm-up outside capture (function attributes, lazy state)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run()
+            ent["graph"] = graph
+            self._eval_graphs[key] = ent
+        ent["lst"].copy_(lst, non_blocking=True)
+        ent["ndvi"].copy_(ndvi, non_blocking=True)
+        ent["graph"].replay()
+        return ent["y"].clone()
 
 
 def bicubic4_cat(lst: torch.Tensor, ndvi: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -310,3 +310,21 @@ def test_step_host_async_matches_graph_step():
     pa = torch.cat([p.detach().reshape(-1) for p in a.parameters()])
     pb = torch.cat([p.detach().reshape(-1) for p in b.parameters()])
     assert torch.equal(pa, pb)
+
+
+def test_eval_graph_replay_matches_eager_and_follows_weight_updates():
+    sd = load_ckpt("1009")
+    m = make_model(sd=sd).eval()
+    g = torch.Generator().manual_seed(8)
+    data = [(torch.randn(b, 1, 64, 64, generator=g).cuda(), torch.randn(b, 1, 256, 256, generator=g).cuda()) for b in (1, 2, 1, 9)]
+    with torch.inference_mode():
+        eager = [m.forward_from_lowres(l, n) for l, n in data]
+        m.enable_eval_graphs(True, max_batch=8)
+        for (l, n), e in zip(data, eager):                 # batch 9 exceeds max_batch and takes the eager path
+            assert torch.equal(m.forward_from_lowres(l, n), e)
+        assert len(m._eval_graphs) == 2
+        m.load_state_dict(load_ckpt("2609"))               # in-place update of the flat parameter buffer: the captured graphs see it
+        m2 = make_model(sd=load_ckpt("2609")).eval()
+        assert torch.equal(m.forward_from_lowres(*data[0]), m2.forward_from_lowres(*data[0]))
+        m.enable_eval_graphs(False)
+        assert torch.equal(m.forward_from_lowres(*data[1]), m2.forward_from_lowres(*data[1]))
