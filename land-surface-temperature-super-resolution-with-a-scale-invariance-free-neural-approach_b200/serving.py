@@ -23,6 +23,7 @@ class PipelinedInference:
         self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
         self._bufs: List[Optional[dict]] = [None] * depth
         self._n = 0
+        self._checked = set()
 
     def _slot(self, lst: torch.Tensor, ndvi: torch.Tensor) -> dict:
         i = self._n % self.depth
@@ -39,8 +40,11 @@ class PipelinedInference:
         """Queue one batch: lst (B,1,h,w), ndvi (B,1,4h,4w) z-scored fp32 in pinned host memory; the (B,1,4h,4w) result lands in out_host
         (pinned) once flush() -- or a later submit() that reuses the slot -- has returned."""
         for t in (lst_host, ndvi_host, out_host):
-            if t.is_cuda or not t.is_pinned() or t.dtype != torch.float32 or not t.is_contiguous():
-                raise SifnnError("PipelinedInference.submit takes contiguous pinned fp32 host tensors")
+            key = (t.data_ptr(), t.numel())
+            if key not in self._checked:   # is_pinned() asks the driver: tens of microseconds per call, so each buffer is vetted once
+                if t.is_cuda or not t.is_pinned() or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise SifnnError("PipelinedInference.submit takes contiguous pinned fp32 host tensors")
+                self._checked.add(key)
         b = self._slot(lst_host, ndvi_host)
         cur = torch.cuda.current_stream(self.dev)
         if b["used"]:
