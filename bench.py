@@ -376,7 +376,7 @@ def run_ours(args):
         if mode in ("infer", "tile"):
             per_kernel = [k for k in per_kernel if "fwd" in k["kernel"]]
         top = max(per_kernel, key=lambda r: r["ms_per_step"])
-        traffic = None
+        traffic, traffic_source = None, None
         try:  # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
             import csv
             name = {"wgrad_tc_kernel": "r1l_ncu_full_wgrad_tc_32x16x256_summary.csv",
@@ -384,12 +384,13 @@ def run_ours(args):
                     "conv3x3_tc_kernel (dgrad)": "r1q_ncu_full_conv3x3_tcx_dgrad_16x16x256_summary.csv",
                     "conv3x3_tc_kernel (fwd)": "r1q_ncu_full_conv3x3_tcx_fwd_32x16x256_summary.csv"}.get(top["kernel"], "r1j_ncu_full_conv3x3_tc_64x32x128_summary.csv")
             vals = {r[0]: r[1] for r in csv.reader(open(os.path.join(ROOT, "profiles", name))) if len(r) >= 2}
-            traffic = {"bytes_per_launch": (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e6,
-                       "launch": name.replace("_summary.csv", ""), "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum"}
+            traffic = (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e6   # bytes of that one launch
+            traffic_source = {"launch": name.replace("_summary.csv", ""), "file": "profiles/" + name,
+                              "metric": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, one launch of the dominant kernel class"}
         except Exception:
             pass
         out["roofline"] = {"bound": top["bound"], "kernel": top["kernel"], "achieved": top["achieved"], "peak": top["peak"], "unit": "TFLOP/s",
-                           "frac": top["frac"], "traffic": traffic,
+                           "frac": top["frac"], "traffic": traffic, "traffic_source": traffic_source,
                            "note": "achieved = algorithmic conv FLOPs of the kernel class over the network's 18 layer shapes / CUDA-event time, measured "
                                    "live through the per-op C-ABI. fp32 peak = this GPU's measured FFMA throughput (sifnn_fp32_peak_kernel, best of 5; not in "
                                    f"MEASURED_PEAKS.json). tensor peak = {how} bf16 {bf16:.0f} TFLOP/s / 2 (TF32) / 3 (3-term split for fp32 parity) = {tensor_eff:.0f}.",
