@@ -53,8 +53,12 @@ struct WtcArgs {
 constexpr int WTC_LOAD_WARP = 0;
 constexpr int WTC_MMA_WARP = 1;
 constexpr int WTC_XF_WARP0 = 2;
-constexpr int WTC_XF_THREADS = 256;
-constexpr int WTC_THREADS = (WTC_XF_WARP0 + 8) * 32;
+#ifndef SIFNN_WTC_XFW
+#define SIFNN_WTC_XFW 8
+#endif
+constexpr int WTC_XFW = SIFNN_WTC_XFW;              // transformer warps
+constexpr int WTC_XF_THREADS = WTC_XFW * 32;
+constexpr int WTC_THREADS = (WTC_XF_WARP0 + WTC_XFW) * 32;
 
 // KC = input channels per CTA (16 or 32; M = 4*KC), N = Cout, R = dy rows per tile, WT = columns per tile
 template <int KC, int N, int R, int WT>
@@ -236,8 +240,8 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
             //      (replicate padding along y)
 #pragma unroll
             for (int i = 0; i < NIT_A; ++i) {
-                const int rr = rrA0 + i * (8 / QH);
-                if (ITEMS_A % WTC_XF_THREADS == 0 || rr < TROWS) {
+                const int rr = rrA0 + i * (WTC_XFW / QH);
+                if ((ITEMS_A % WTC_XF_THREADS == 0 && WTC_XFW == 8) || rr < TROWS) {
                     const int rj = min(max(y0 + rr - 1, 0), H - 1) - (y0 - 1);
                     const float* src = rawx + rj * (KC * WT) + a_src;
                     float hi[4], lo[4];
@@ -261,8 +265,8 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
             const int gx = x0 + col;
 #pragma unroll
             for (int i = 0; i < NIT_B; ++i) {
-                const int r = rB0 + i * (8 / OQH);
-                if (ITEMS_B % WTC_XF_THREADS == 0 || r < R) {
+                const int r = rB0 + i * (WTC_XFW / OQH);
+                if ((ITEMS_B % WTC_XF_THREADS == 0 && WTC_XFW == 8) || r < R) {
                     const float* src = rawd + r * (N * DYW) + b_src;
                     float v[3][4];
 #pragma unroll
