@@ -47,12 +47,7 @@ struct LossArgs {
     int B, H, W;
 };
 
-__constant__ float c_sobel[4][9] = {
-    {1, 2, 1, 0, 0, 0, -1, -2, -1},
-    {1, 0, -1, 2, 0, -2, 1, 0, -1},
-    {2, 1, 0, 1, 0, -1, 0, -1, -2},
-    {0, 1, 2, -1, 0, 1, -2, -1, 0},
-};
+// the four predefined 3x3 gradient filters of train_model_B_predef_filters.py:38-42 are compile-time tables inside the kernel (SB)
 
 template <int KIND>
 __global__ void __launch_bounds__(LNT, 1) loss_kernel(const LossArgs a) {
@@ -128,23 +123,33 @@ __global__ void __launch_bounds__(LNT, 1) loss_kernel(const LossArgs a) {
     // ---- P3: perceptual residual e and huber'(e) ----------------------------------------------------
     if (KIND == 1) {
         constexpr int E = T + 2;  // 66
-        for (int idx = tid; idx < 4 * E * E; idx += LNT) {
-            const int f = idx / (E * E);
-            const int rem = idx - f * (E * E);
-            const int rr = rem / E, cc = rem - rr * E;
+        // one item = one pixel of the 66x66 halo region, all four filters: the nine x values are read once and the filter coefficients are
+        // compile-time constants (half of them zero), instead of one item per (filter, pixel) with dynamically indexed coefficients
+        for (int idx = tid; idx < E * E; idx += LNT) {
+            const int rr = idx / E, cc = idx - rr * E;
             const int r = r0 - 1 + rr, c = c0 - 1 + cc;
-            float psi = 0.f;
+            float psi[4] = {0.f, 0.f, 0.f, 0.f};
             if (r >= 0 && r < H && c >= 0 && c < W) {
                 const float* xp = X + (rr + HALO - 2) * TS + (cc + HALO - 2);  // x[r-1][c-1]
-                float e = 0.f;
+                float xv[9];
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) e = fmaf(c_sobel[f][ky * 3 + kx], xp[ky * TS + kx], e);
-                psi = c_p * huber_grad(e);
-                if (rr >= 1 && rr <= T && cc >= 1 && cc <= T) acc_p += huber(e);
+                    for (int kx = 0; kx < 3; ++kx) xv[ky * 3 + kx] = xp[ky * TS + kx];
+                const bool inner = rr >= 1 && rr <= T && cc >= 1 && cc <= T;
+                constexpr float SB[4][9] = {{1, 2, 1, 0, 0, 0, -1, -2, -1}, {1, 0, -1, 2, 0, -2, 1, 0, -1}, {2, 1, 0, 1, 0, -1, 0, -1, -2}, {0, 1, 2, -1, 0, 1, -2, -1, 0}};
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    float e = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t)
+                        if (SB[f][t] != 0.f) e = fmaf(SB[f][t], xv[t], e);
+                    psi[f] = c_p * huber_grad(e);
+                    if (inner) acc_p += huber(e);
+                }
             }
-            PE[idx] = psi;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) PE[f * E * E + idx] = psi[f];
         }
     } else {
         constexpr int E = T + 8;  // 72
@@ -228,13 +233,14 @@ __global__ void __launch_bounds__(LNT, 1) loss_kernel(const LossArgs a) {
         }
         if (KIND == 1) {
             constexpr int E = T + 2;
+            constexpr float SB[4][9] = {{1, 2, 1, 0, 0, 0, -1, -2, -1}, {1, 0, -1, 2, 0, -2, 1, 0, -1}, {2, 1, 0, 1, 0, -1, 0, -1, -2}, {0, 1, 2, -1, 0, 1, -2, -1, 0}};
 #pragma unroll
             for (int f = 0; f < 4; ++f)
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx)
-                        g = fmaf(c_sobel[f][ky * 3 + kx], PE[f * E * E + (rr + 2 - ky) * E + (cc + 2 - kx)], g);
+                        if (SB[f][ky * 3 + kx] != 0.f) g = fmaf(SB[f][ky * 3 + kx], PE[f * E * E + (rr + 2 - ky) * E + (cc + 2 - kx)], g);
         } else {
             constexpr int E = T + 8;
             const float* TMP2 = PE + E * E + TS * E;
