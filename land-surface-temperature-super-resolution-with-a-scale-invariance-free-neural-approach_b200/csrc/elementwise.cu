@@ -324,6 +324,13 @@ __global__ void __launch_bounds__(256) upcat_bwd_low_tiled_kernel(const float* _
         const int r = tid >> 2, e = tid & 3;
         in_s[r * (Wo + 4) + (e < 2 ? e : Wo + e)] = 0.f;
     }
+    __shared__ float wy_s[UPB_TL][6];      // the y weights depend on the row only: one thread per low-resolution row computes them once
+    if (tid >= 128 && tid < 128 + UPB_TL) {
+        float wv[6];
+        up_gather_weights(i_lo + tid - 128, H, ry, wv);
+#pragma unroll
+        for (int t = 0; t < 6; ++t) wy_s[tid - 128][t] = wv[t];
+    }
     __syncthreads();
     const int k = tid & (W - 1), rg = tid / W, nrg = 256 / W;
     float wx[6];
@@ -337,11 +344,9 @@ __global__ void __launch_bounds__(256) upcat_bwd_low_tiled_kernel(const float* _
     for (int il = rg; il < UPB_TL; il += nrg) {
         const int i = i_lo + il;
         if (i >= H) break;
-        float wy[6];
-        up_gather_weights(i, H, ry, wy);
         float acc = 0.f;
 #pragma unroll
-        for (int t = 0; t < 6; ++t) acc = fmaf(wy[t], tmp[(2 * il + t) * W + k], acc);
+        for (int t = 0; t < 6; ++t) acc = fmaf(wy_s[il][t], tmp[(2 * il + t) * W + k], acc);
         dlow[((size_t)plane * H + i) * W + k] = acc;
     }
 }

@@ -32,3 +32,12 @@ print(f"bn_relu_bwd (reduce + apply) 16@256^2 B=32: {t * 1e6:.1f} us, algorithmi
 t = timed(lambda: loss_fwd_bwd("sr1", y, lst, ndvi, 0.99, -0.5, want_grad=True))
 lb = B * 802816
 print(f"loss_kernel SR1 B=32: {t * 1e6:.1f} us, algorithmic {lb / 1e6:.1f} MB -> {lb / t / 1e9:.0f} GB/s")
+go = torch.randn(B, 32, 256, 256, device="cuda")
+t = timed(lambda: ops.upcat_bwd(go, 16))
+ub = (B * 32 * 256 * 256 + B * 16 * 128 * 128 + B * 16 * 256 * 256) * 4
+print(f"upcat_bwd (low adjoint + skip copy) 16@128^2 <- 32@256^2 B=32: {t * 1e6:.1f} us, algorithmic {ub / 1e6:.0f} MB -> {ub / t / 1e9:.0f} GB/s")
+low, skip = torch.randn(B, 16, 128, 128, device="cuda"), torch.randn(B, 16, 256, 256, device="cuda")
+s16, h16 = torch.rand(16, device="cuda") + 0.5, torch.randn(16, device="cuda") * 0.1
+t = timed(lambda: ops.act_upcat_fwd(low, s16, h16, skip, s16, h16))
+fb = (B * 16 * 128 * 128 + B * 16 * 256 * 256 + B * 32 * 256 * 256) * 4
+print(f"act_upcat 16@128^2 + 16@256^2 -> 32@256^2 B=32: {t * 1e6:.1f} us, algorithmic {fb / 1e6:.0f} MB -> {fb / t / 1e9:.0f} GB/s")
