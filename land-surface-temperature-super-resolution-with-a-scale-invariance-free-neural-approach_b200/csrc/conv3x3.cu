@@ -545,17 +545,35 @@ __global__ void __launch_bounds__(256) dgrad_border_cols_kernel(const float* __r
     const int q = side ? W - 1 : 0, kx = side ? 2 : 0;
     const size_t plane = (size_t)H * W;
     const float* dyb = dy + (size_t)b * Cout * plane + q;
-    for (int idx = tid; idx < Cout * (BCOL_ROWS + 2); idx += 256) {
-        const int o = idx / (BCOL_ROWS + 2), r = idx - o * (BCOL_ROWS + 2);
-        const int y = p0 - 1 + r;
-        dys[idx] = (y >= 0 && y < H) ? __ldg(dyb + (size_t)o * plane + (size_t)y * W) : 0.f;
+    // the read half of the dx update is issued first: its DRAM latency hides behind the staging below
+    const int p = p0 + lane;
+    float dxv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int k = kc0 + 4 * warp + u;
+        dxv[u] = (p < H && k < Cin) ? dx[((size_t)b * Cin + k) * plane + (size_t)p * W + q] : 0.f;
+    }
+    const int n_dy = Cout * (BCOL_ROWS + 2);
+    for (int base = 0; base < n_dy; base += 4 * 256) {     // four independent sector requests in flight per thread
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * 256 + tid;
+            const int o = idx / (BCOL_ROWS + 2), r = idx - o * (BCOL_ROWS + 2);
+            const int y = p0 - 1 + r;
+            v[u] = (idx < n_dy && y >= 0 && y < H) ? __ldg(dyb + (size_t)o * plane + (size_t)y * W) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * 256 + tid;
+            if (idx < n_dy) dys[idx] = v[u];
+        }
     }
     for (int idx = tid; idx < Cout * 96; idx += 256) {
         const int k = idx & 31, ky = (idx >> 5) % 3, o = idx / 96;
         wsm[idx] = (kc0 + k < Cin) ? __ldg(w + ((size_t)o * Cin + kc0 + k) * 9 + ky * 3 + kx) : 0.f;
     }
     __syncthreads();
-    const int p = p0 + lane;
     const bool top = corners && p == 0, bot = corners && p == H - 1;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
@@ -576,7 +594,7 @@ __global__ void __launch_bounds__(256) dgrad_border_cols_kernel(const float* __r
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int k = kc0 + 4 * warp + u;
-            if (k < Cin) dx[((size_t)b * Cin + k) * plane + (size_t)p * W + q] += acc[u];
+            if (k < Cin) dx[((size_t)b * Cin + k) * plane + (size_t)p * W + q] = dxv[u] + acc[u];
         }
     }
 }
