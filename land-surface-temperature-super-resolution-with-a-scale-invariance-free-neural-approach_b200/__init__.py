@@ -17,6 +17,7 @@ from .parallel import block_partition, shard_batch, BucketedAllReduce  # noqa: F
 from .tile import super_resolve_tile, window_list  # noqa: F401
 from .serving import PipelinedInference  # noqa: F401
 from .fit import model_checkpoint, fit, train_epoch, eval_epoch, save_model, load_model, save_metrics  # noqa: F401
+from .dataset import ModisDatasetB, PinnedBatchLoader, read_geotiff, save_geotiff, upsampling  # noqa: F401
 
 
 

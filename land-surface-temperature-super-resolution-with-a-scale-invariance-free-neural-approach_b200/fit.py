@@ -26,6 +26,7 @@ from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 import torch
 
 from .trainer import Trainer
+from .model import bicubic4_cat
 from . import ops
 
 Batch = Tuple[torch.Tensor, torch.Tensor, torch.Tensor]   # (lst, lst_up, ndvi) as ModisDatasetB.__getitem__ collates them
@@ -87,6 +88,13 @@ def _epoch_mean(sums: torch.Tensor, n_batches: int) -> Tuple[float, float, float
     return ds, pl, loss
 
 
+def _to_device(dev, lst, lst_up, ndvi):
+    """Batches come as tensors or numpy arrays, on the host (pinned: the copies are asynchronous) or already on the device;
+    ``lst_up`` may be None (``PinnedBatchLoader(with_upsampled=False)``): the device front-end recomputes it."""
+    mv = lambda t: None if t is None else torch.as_tensor(t).to(dev, non_blocking=True)  # noqa: E731
+    return mv(lst), mv(lst_up), mv(ndvi)
+
+
 def train_epoch(trainer: Trainer, batches: Iterable[Batch], device=None,
                 quality=None):
     """``train_step`` of the reference: one pass over the loader in train mode; returns the epoch means
@@ -99,10 +107,12 @@ def train_epoch(trainer: Trainer, batches: Iterable[Batch], device=None,
     qsum = torch.zeros(2, dtype=torch.float64, device=dev)
     n = 0
     for lst, lst_up, ndvi in batches:
-        lst, lst_up, ndvi = lst.to(dev, non_blocking=True), lst_up.to(dev, non_blocking=True), ndvi.to(dev, non_blocking=True)
+        lst, lst_up, ndvi = _to_device(dev, lst, lst_up, ndvi)
         losses, y = trainer._step_impl(lst, ndvi, lst_up)
         sums += losses
         if qf is not None:
+            if lst_up is None:
+                lst_up = bicubic4_cat(lst, ndvi)[:, :1]
             qsum += torch.as_tensor(qf(y, lst_up), dtype=torch.float64, device=dev)
         n += 1
     ds, pl, loss = _epoch_mean(sums, n)
@@ -121,9 +131,11 @@ def eval_epoch(trainer: Trainer, batches: Iterable[Batch], device=None,
     qsum = torch.zeros(2, dtype=torch.float64, device=dev)
     n = 0
     for lst, lst_up, ndvi in batches:
-        lst, lst_up, ndvi = lst.to(dev, non_blocking=True), lst_up.to(dev, non_blocking=True), ndvi.to(dev, non_blocking=True)
+        lst, lst_up, ndvi = _to_device(dev, lst, lst_up, ndvi)
         sums += trainer.evaluate(lst, ndvi, lst_up)
         if qf is not None:
+            if lst_up is None:
+                lst_up = bicubic4_cat(lst, ndvi)[:, :1]
             was = m.training
             m.eval()
             y = m(torch.cat((lst_up, ndvi), dim=1))
