@@ -192,12 +192,12 @@ def kernel_rooflines(batch, fp32_peak, tensor_peak_eff):
         if use_tc and co <= 64 and lib.sifnn_conv3x3_tc_supported(ci, co, hw, hw):
             add("conv3x3_tc_kernel (fwd)", timed(lambda: ops.conv3x3_fwd_tc(x, w)), fl)
         else:
-            add("conv3x3_kernel (fwd, SIMT)", timed(lambda: ops.conv3x3_fwd(x, w)), fl)
+            add("conv3x3_kernel 2->16 + conv3x3_to1_kernel 16->1 (fwd, SIMT)", timed(lambda: ops.conv3x3_fwd(x, w)), fl)
         if i > 0:
             if use_tc and lib.sifnn_conv3x3_tc_supported(co, ci, hw, hw):
                 add("conv3x3_tc_kernel (dgrad)", timed(lambda: ops.conv3x3_dgrad_tc(dy, w)), fl)
             else:
-                add("conv3x3_kernel (dgrad, SIMT)", timed(lambda: ops.conv3x3_dgrad(dy, w)), fl)
+                add("dgrad_from1_kernel 16->1 (dgrad, SIMT)", timed(lambda: ops.conv3x3_dgrad(dy, w)), fl)
         if use_tc and lib.sifnn_conv3x3_wgrad_tc_supported(ci, co, hw, hw):
             add("wgrad_tc_kernel", timed(lambda: ops.conv3x3_wgrad_tc(x, dy)), fl)
         else:
