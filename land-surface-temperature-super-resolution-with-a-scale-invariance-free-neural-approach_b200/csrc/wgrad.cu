@@ -338,12 +338,129 @@ __global__ void __launch_bounds__((O_CHUNK / OT) * (K_CHUNK / KT) * 32, 1) wgrad
     }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int S) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// out[i] = sum_s partial[s][i] in a fixed order (deterministic): 8 slice-strided sums per output, combined in order.  Outputs
+// n .. n + nb - 1 are the bias gradient (own partial array), so one launch finishes both.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int S,
+                                                           const float* __restrict__ bias_partial, float* __restrict__ bias_out, int nb) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
+    const float* src = i < n ? partial + i : bias_partial + (i - n);
+    const int stride = i < n ? n : nb;
     float acc = 0.f;
-    for (int s = 0; s < S; ++s) acc += partial[(size_t)s * n + i];
-    out[i] = acc;
+    if (i < n + nb)
+        for (int s = ty; s < S; s += 8) acc += __ldg(src + (size_t)s * stride);
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && i < n + nb) {
+        float t = red[0][tx];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) t += red[j][tx];
+        if (i < n) out[i] = t;
+        else bias_out[i - n] = t;
+    }
+}
+
+// ---- one output channel (the network's `outlay`): dW[k][ky][kx] = sum dy[y][x] * act(in)[k][clamp(y+ky-1)][clamp(x+kx-1)] ----
+// The register-tiled kernel above needs many (o, k) pairs per warp to amortise its shared-memory reads; with one output channel
+// it is load-bound.  Here a thread owns 4 columns x 8 rows of dy (kept in registers for all input channels) and, per channel,
+// slides over the 10 input rows straight from global memory like conv3x3_to1_kernel: 288 FMAs into 9 sums, which are reduced
+// over the warp by shuffles and added to the warp's row of shared accumulators by lane 0.  CTAs stride over the pixel blocks; a
+// CTA's 4 warp rows are summed in order into its partial, the partials by wgrad_reduce_kernel: deterministic, no atomics.
+constexpr int W1_MAXK = 64;
+constexpr int W1_ROWS = 8;
+
+template <bool AFFINE>
+__global__ void __launch_bounds__(128, 4) wgrad_to1_kernel(const WgradArgs a) {
+    __shared__ float red[4][W1_MAXK * 9 + 1];
+    __shared__ float sc_s[W1_MAXK], sh_s[W1_MAXK];
+    const int K = a.K, H = a.H, W = a.W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 4 * (W1_MAXK * 9 + 1); i += 128) (&red[0][0])[i] = 0.f;
+    if (AFFINE)
+        for (int i = tid; i < K; i += 128) { sc_s[i] = __ldg(a.in_scale + i); sh_s[i] = __ldg(a.in_shift + i); }
+    __syncthreads();
+    const int w4 = W >> 2;
+    const int bands = (H + W1_ROWS - 1) / W1_ROWS;
+    const int total = a.B * bands * w4;
+    const size_t plane = (size_t)H * W;
+    float bsum = 0.f;
+    for (int base = blockIdx.x * 128; base < total; base += gridDim.x * 128) {
+        const int u = base + tid;
+        const bool live = u < total;
+        const int uu = live ? u : 0;
+        const int x0 = (uu % w4) << 2;
+        const int band = (uu / w4) % bands;
+        const int b = uu / (w4 * bands);
+        const int y0 = band * W1_ROWS;
+        const float* dyb = a.dy + (size_t)b * plane;
+        float d[W1_ROWS][4];
+#pragma unroll
+        for (int r = 0; r < W1_ROWS; ++r) {
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && y0 + r < H) m = __ldg(reinterpret_cast<const float4*>(dyb + (size_t)(y0 + r) * W + x0));
+            d[r][0] = m.x; d[r][1] = m.y; d[r][2] = m.z; d[r][3] = m.w;
+            bsum += (m.x + m.y) + (m.z + m.w);
+        }
+        const int xl = max(x0 - 1, 0), xr = min(x0 + 4, W - 1);
+        int rowoff[W1_ROWS + 2];
+#pragma unroll
+        for (int r = 0; r < W1_ROWS + 2; ++r) rowoff[r] = min(max(y0 - 1 + r, 0), H - 1) * W;
+        const float* in_b = a.in + (size_t)b * K * plane;
+#pragma unroll 1
+        for (int ci = 0; ci < K; ++ci) {
+            const float* ip = in_b + (size_t)ci * plane;
+            const float sc = AFFINE ? sc_s[ci] : 1.f, sh = AFFINE ? sh_s[ci] : 0.f;
+            float v[W1_ROWS + 2][6];
+#pragma unroll
+            for (int r = 0; r < W1_ROWS + 2; ++r) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(ip + rowoff[r] + x0));
+                v[r][0] = __ldg(ip + rowoff[r] + xl);
+                v[r][1] = m.x; v[r][2] = m.y; v[r][3] = m.z; v[r][4] = m.w;
+                v[r][5] = __ldg(ip + rowoff[r] + xr);
+            }
+            if (AFFINE) {
+#pragma unroll
+                for (int r = 0; r < W1_ROWS + 2; ++r)
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) v[r][i] = sifnn::act_affine_relu(v[r][i], sc, sh);
+            }
+            float sum[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) sum[t] = 0.f;
+#pragma unroll
+            for (int r = 0; r < W1_ROWS; ++r)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) sum[ky * 3 + kx] = fmaf(d[r][i], v[r + ky][i + kx], sum[ky * 3 + kx]);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) sum[t] = sifnn::warp_sum(sum[t]);
+            if (lane == 0) {
+#pragma unroll
+                for (int t = 0; t < 9; ++t) red[warp][ci * 9 + t] += sum[t];
+            }
+        }
+    }
+    bsum = sifnn::warp_sum(bsum);
+    if (lane == 0) red[warp][W1_MAXK * 9] = bsum;
+    __syncthreads();
+    const int n = K * 9;
+    for (int i = tid; i < n; i += 128)
+        a.partial[(size_t)blockIdx.x * n + i] = ((red[0][i] + red[1][i]) + red[2][i]) + red[3][i];
+    if (tid == 0)
+        a.bias_partial[blockIdx.x] = ((red[0][W1_MAXK * 9] + red[1][W1_MAXK * 9]) + red[2][W1_MAXK * 9]) + red[3][W1_MAXK * 9];
+}
+
+static bool to1_wgrad_eligible(int K, int O, int W, const float* in, const float* dy) {
+    return O == 1 && K <= W1_MAXK && W % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0;
+}
+
+static int to1_wgrad_ctas(int B, int H, int W) {
+    const int units = B * ((H + W1_ROWS - 1) / W1_ROWS) * (W / 4);
+    return max(1, min(4 * sifnn::num_sms(), (units + 127) / 128));
 }
 
 struct Plan {
@@ -393,7 +510,9 @@ int launch_wgrad(const WgradArgs& a, const Plan& p, bool affine, cudaStream_t st
 extern "C" size_t sifnn_conv3x3_wgrad_workspace(int B, int Cin, int Cout, int H, int W) {
     if (B <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return 0;
     const Plan p = make_plan(B, Cin, Cout, H, W);
-    return ((size_t)p.S * Cout * Cin * 9 + (size_t)p.S * Cout) * sizeof(float);
+    size_t S = (size_t)p.S;
+    if (Cout == 1 && Cin <= W1_MAXK && W % 4 == 0) S = max(S, (size_t)to1_wgrad_ctas(B, H, W));   // wgrad_to1_kernel: one partial per CTA
+    return (S * Cout * Cin * 9 + S * Cout) * sizeof(float);
 }
 
 extern "C" int sifnn_conv3x3_wgrad(const float* in, const float* in_scale, const float* in_shift, const float* dy,
@@ -413,15 +532,19 @@ extern "C" int sifnn_conv3x3_wgrad(const float* in, const float* in_scale, const
     a.tiles_x = p.tiles_x; a.tiles_per_img = p.tiles_x * p.tiles_y; a.total_tiles = p.total_tiles;
     a.vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
     const bool affine = in_scale != nullptr;
-    if (p.variant == 2) SIFNN_TRY((launch_wgrad<1, 1, 1, 16, true>(a, p, affine, st)));
+    int S = p.S;
+    if (to1_wgrad_eligible(Cin, Cout, W, in, dy)) {
+        S = to1_wgrad_ctas(B, H, W);
+        a.bias_partial = a.partial + (size_t)S * Cin * 9;
+        if (affine) wgrad_to1_kernel<true><<<S, 128, 0, st>>>(a);
+        else wgrad_to1_kernel<false><<<S, 128, 0, st>>>(a);
+        SIFNN_TRY(sifnn::check_launch("wgrad_to1_kernel"));
+    } else if (p.variant == 2) SIFNN_TRY((launch_wgrad<1, 1, 1, 16, true>(a, p, affine, st)));
     else if (p.variant == 1) SIFNN_TRY((launch_wgrad<2, 1, 16, 2, false>(a, p, affine, st)));
     else SIFNN_TRY((launch_wgrad<4, 2, 16, 8, false>(a, p, affine, st)));
     const int n = Cout * Cin * 9;
-    wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.partial, dw, n, p.S);
+    const int nb = dbias ? Cout : 0;
+    wgrad_reduce_kernel<<<(n + nb + 31) / 32, 256, 0, st>>>(a.partial, dw, n, S, a.bias_partial, dbias, nb);
     SIFNN_TRY(sifnn::check_launch("wgrad_reduce_kernel"));
-    if (dbias) {
-        wgrad_reduce_kernel<<<1, 32, 0, st>>>(a.bias_partial, dbias, Cout, p.S);
-        SIFNN_TRY(sifnn::check_launch("wgrad_reduce_kernel(bias)"));
-    }
     return 0;
 }

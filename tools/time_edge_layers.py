@@ -46,3 +46,11 @@ F.conv2d(F.pad(xr, (1, 1, 1, 1), mode="replicate"), w1).backward(dy1[:4])
 dxo = ops.conv3x3_dgrad(dy1[:4].contiguous(), w1)
 print("16->1 dgrad rel err", float((dxo - xr.grad).abs().max() / xr.grad.abs().max()))
 print(f"16->1 dgrad (1 -> 16 channels):     {timeit(lambda: ops.conv3x3_dgrad(dy1, w1)):7.1f} us   HBM floor {(dy1.numel() + x16.numel()) * 4 / 6.5e12 * 1e6:5.1f} us")
+xa = torch.relu(x16[:4] * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+wr = w1.clone().requires_grad_(True); br = bias.clone().requires_grad_(True)
+F.conv2d(F.pad(xa, (1, 1, 1, 1), mode="replicate"), wr, br).backward(dy1[:4])
+dw, db = ops.conv3x3_wgrad(x16[:4].contiguous(), dy1[:4].contiguous(), sc, sh, want_bias=True)
+print("16->1 wgrad rel err", float((dw - wr.grad).abs().max() / wr.grad.abs().max()), "bias", float((db - br.grad).abs().max() / br.grad.abs().max()))
+print(f"16->1 wgrad (+ prologue, bias grad):  {timeit(lambda: ops.conv3x3_wgrad(x16, dy1, sc, sh, want_bias=True)):7.1f} us   HBM floor {(x16.numel() + dy1.numel()) * 4 / 6.5e12 * 1e6:5.1f} us")
+dy16 = torch.randn(B, 16, H, H, device="cuda", generator=g)
+print(f"2->16 wgrad:                         {timeit(lambda: ops.conv3x3_wgrad(x2, dy16)):7.1f} us   HBM floor {(x2.numel() + dy16.numel()) * 4 / 6.5e12 * 1e6:5.1f} us")
