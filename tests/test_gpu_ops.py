@@ -211,3 +211,32 @@ def test_bad_arguments_raise():
         ops.conv3x3_fwd(x, torch.zeros(4, 2, 3, 3))  # CPU tensors: no fallback
     with pytest.raises(sifnn_b200.SifnnError):
         sifnn_b200._lib.call("sifnn_conv3x3_fwd", None, None, None, None, None, None, None, 1, 1, 1, 8, 8, None)
+
+
+# The output layer's dedicated kernels (conv3x3_to1 / dgrad_from1 / wgrad_to1): partial row bands, the smallest image, several
+# column groups per warp straddling rows, many channels, and widths the kernels do not take (generic path, same contract).
+TO1_SHAPES = [(1, 16, 2, 4), (2, 16, 5, 8), (3, 7, 10, 12), (1, 64, 9, 36), (2, 3, 33, 260), (5, 16, 13, 20), (1, 16, 6, 10), (1, 70, 8, 8)]
+
+
+@pytest.mark.parametrize("shape", TO1_SHAPES)
+def test_single_output_channel_layer(shape):
+    B, Cin, H, W = shape
+    x, w, b = rnd(B, Cin, H, W, seed=71), rnd(1, Cin, 3, 3, seed=72, scale=0.2), rnd(1, seed=73)
+    sc, sh = 1 + 0.3 * rnd(Cin, seed=74), 0.2 * rnd(Cin, seed=75)
+    dy = rnd(B, 1, H, W, seed=76)
+    # forward, plain and with the BatchNorm + ReLU prologue
+    assert rel_err(ops.conv3x3_fwd(x.cuda(), w.cuda(), b.cuda()), ref_conv(x, w, b)) < TOL
+    xa = torch.relu(x.double() * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1))
+    assert rel_err(ops.conv3x3_fwd(x.cuda(), w.cuda(), b.cuda(), sc.cuda(), sh.cuda()), ref_conv(xa, w, b)) < TOL
+    # data gradient (padding adjoint folded in) and weight / bias gradient
+    xr = xa.clone().requires_grad_(True)
+    wr = w.double().clone().requires_grad_(True)
+    br = b.double().clone().requires_grad_(True)
+    (F.conv2d(F.pad(xr, (1, 1, 1, 1), mode="replicate"), wr, br) * dy.double()).sum().backward()
+    assert rel_err(ops.conv3x3_dgrad(dy.cuda(), w.cuda()), xr.grad) < TOL
+    dw, db = ops.conv3x3_wgrad(x.cuda(), dy.cuda(), sc.cuda(), sh.cuda(), want_bias=True)
+    assert rel_err(dw, wr.grad) < TOL and rel_err(db, br.grad) < TOL
+    dw2 = ops.conv3x3_wgrad(x.cuda(), dy.cuda())
+    wr2 = w.double().clone().requires_grad_(True)
+    (ref_conv(x, wr2) * dy.double()).sum().backward()
+    assert rel_err(dw2, wr2.grad) < TOL
