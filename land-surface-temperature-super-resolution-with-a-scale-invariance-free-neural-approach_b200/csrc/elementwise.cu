@@ -282,8 +282,11 @@ __global__ void __launch_bounds__(256) upcat_bwd_low_kernel(const float* __restr
 }
 
 // Same adjoint, tiled: one CTA = (plane, band of 8 low-resolution rows).  The 20 contributing rows of dout are staged in shared memory with
-// coalesced float4 loads, reduced along x (6-tap gather per low-resolution column, weights computed once per thread) and then along y.
-// W <= 128 and W a power of two (the decoder's 32 / 64 / 128); other shapes take the generic kernel above.
+// coalesced 16-byte loads and stores; a thread then owns one low-resolution column k and LR of the band's rows: it reduces the
+// 2 LR + 4 staged rows it needs along x into registers (6-tap gather, weights computed once per thread) and finishes along y from
+// those registers -- one barrier, no intermediate buffer.  (The first version wrote the x pass back to shared memory, staged with
+// scalar stores and divided by W at run time: ncu showed 78 % issue activity and 1.6 M store bank conflicts, 70 us at 16 x 128^2, B = 32.)
+// W in {32, 64, 128} (the decoder's levels; LR = W / 32); other shapes take the generic kernel above.
 constexpr int UPB_TL = 8, UPB_NR = 2 * UPB_TL + 4;
 __device__ __forceinline__ void up_gather_weights(int i, int n_in, float r, float* wv) {
     // weight of output index 2i-2+t (t = 0..5) on low-resolution index i
@@ -299,32 +302,31 @@ __device__ __forceinline__ void up_gather_weights(int i, int n_in, float r, floa
         wv[t] = wgt;
     }
 }
-__global__ void __launch_bounds__(256) upcat_bwd_low_tiled_kernel(const float* __restrict__ dout, float* __restrict__ dlow, int C1, int C2, int H, int W,
+template <int LR>
+__global__ void __launch_bounds__(256) upcat_bwd_low_tiled_kernel(const float* __restrict__ dout, float* __restrict__ dlow, int C1, int C2, int H,
                                                                   float ry, float rx) {
-    extern __shared__ __align__(16) float usm[];
-    const int Wo = 2 * W, Ho = 2 * H;
-    float* in_s = usm;                    // [UPB_NR][Wo + 4]: column x at index x + 2 (two zero columns each side)
-    float* tmp = usm + UPB_NR * (Wo + 4);  // [UPB_NR][W]
+    constexpr int W = 32 * LR, Wo = 2 * W, Wq = Wo / 4, STRIDE = Wo + 8;   // staged row: column x at index x + 4, zeros at -2, -1, Wo, Wo + 1
+    __shared__ __align__(16) float in_s[UPB_NR * STRIDE];
+    __shared__ float wy_s[UPB_TL][6];      // the y weights depend on the row only: one thread per low-resolution row computes them once
+    const int Ho = 2 * H;
     const int tid = threadIdx.x;
     const int plane = blockIdx.y;          // b * C1 + c
     const int b = plane / C1, c = plane - b * C1;
     const int i_lo = blockIdx.x * UPB_TL;
     const int y_lo = 2 * i_lo - 2;
     const float* g = dout + ((size_t)b * (C1 + C2) + c) * Ho * Wo;
-    const int Wq = Wo >> 2;
+#pragma unroll
     for (int idx = tid; idx < UPB_NR * Wq; idx += 256) {
-        const int r = idx / Wq, x4 = idx - r * Wq;
+        const int r = idx / Wq, x4 = idx % Wq;
         const int y = y_lo + r;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (y >= 0 && y < Ho) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)y * Wo) + x4);
-        float* d = in_s + r * (Wo + 4) + 2 + 4 * x4;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        *reinterpret_cast<float4*>(in_s + r * STRIDE + 4 + 4 * x4) = v;
     }
     if (tid < UPB_NR * 4) {
         const int r = tid >> 2, e = tid & 3;
-        in_s[r * (Wo + 4) + (e < 2 ? e : Wo + e)] = 0.f;
+        in_s[r * STRIDE + (e < 2 ? 2 + e : Wo + 2 + e)] = 0.f;
     }
-    __shared__ float wy_s[UPB_TL][6];      // the y weights depend on the row only: one thread per low-resolution row computes them once
     if (tid >= 128 && tid < 128 + UPB_TL) {
         float wv[6];
         up_gather_weights(i_lo + tid - 128, H, ry, wv);
@@ -332,22 +334,25 @@ __global__ void __launch_bounds__(256) upcat_bwd_low_tiled_kernel(const float* _
         for (int t = 0; t < 6; ++t) wy_s[tid - 128][t] = wv[t];
     }
     __syncthreads();
-    const int k = tid & (W - 1), rg = tid / W, nrg = 256 / W;
+    const int k = tid % W, il0 = (tid / W) * LR;      // this thread: column k, band rows il0 .. il0 + LR - 1
     float wx[6];
     up_gather_weights(k, W, rx, wx);
-    for (int r = rg; r < UPB_NR; r += nrg) {
-        const float2* p = reinterpret_cast<const float2*>(in_s + r * (Wo + 4) + 2 * k);   // columns 2k-2 .. 2k+3
-        const float2 a0 = p[0], a1 = p[1], a2 = p[2];
-        tmp[r * W + k] = fmaf(wx[0], a0.x, fmaf(wx[1], a0.y, fmaf(wx[2], a1.x, fmaf(wx[3], a1.y, fmaf(wx[4], a2.x, wx[5] * a2.y)))));
-    }
-    __syncthreads();
-    for (int il = rg; il < UPB_TL; il += nrg) {
-        const int i = i_lo + il;
-        if (i >= H) break;
-        float acc = 0.f;
+    float xr[2 * LR + 4];                              // staged rows 2 il0 .. 2 il0 + 2 LR + 3, reduced along x
 #pragma unroll
-        for (int t = 0; t < 6; ++t) acc = fmaf(wy_s[il][t], tmp[(2 * il + t) * W + k], acc);
-        dlow[((size_t)plane * H + i) * W + k] = acc;
+    for (int r = 0; r < 2 * LR + 4; ++r) {
+        const float2* p = reinterpret_cast<const float2*>(in_s + (2 * il0 + r) * STRIDE + 2 * k + 2);   // columns 2k-2 .. 2k+3
+        const float2 a0 = p[0], a1 = p[1], a2 = p[2];
+        xr[r] = fmaf(wx[0], a0.x, fmaf(wx[1], a0.y, fmaf(wx[2], a1.x, fmaf(wx[3], a1.y, fmaf(wx[4], a2.x, wx[5] * a2.y)))));
+    }
+#pragma unroll
+    for (int l = 0; l < LR; ++l) {
+        const int i = i_lo + il0 + l;
+        if (i < H) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < 6; ++t) acc = fmaf(wy_s[il0 + l][t], xr[2 * l + t], acc);
+            dlow[((size_t)plane * H + i) * W + k] = acc;
+        }
     }
 }
 
@@ -511,10 +516,11 @@ extern "C" int sifnn_upcat_bwd(const float* dout, float* dlow, float* dskip, int
     SIFNN_REQUIRE(B > 0 && C1 > 0 && C2 > 0 && H > 0 && W > 0 && (H * W) % 1 == 0, "upcat_bwd: bad shape");
     cudaStream_t st = sifnn::as_stream(stream);
     const long long total = (long long)B * C1 * H * W;
-    if (W <= 128 && W >= 8 && (W & (W - 1)) == 0 && (long long)B * C1 <= 65535) {
-        const size_t smem = (size_t)UPB_NR * (2 * W + 4 + W) * sizeof(float);
+    if ((W == 32 || W == 64 || W == 128) && (long long)B * C1 <= 65535) {
         dim3 grid((H + UPB_TL - 1) / UPB_TL, B * C1);
-        upcat_bwd_low_tiled_kernel<<<grid, 256, smem, st>>>(dout, dlow, C1, C2, H, W, up_ratio(H), up_ratio(W));
+        if (W == 128) upcat_bwd_low_tiled_kernel<4><<<grid, 256, 0, st>>>(dout, dlow, C1, C2, H, up_ratio(H), up_ratio(W));
+        else if (W == 64) upcat_bwd_low_tiled_kernel<2><<<grid, 256, 0, st>>>(dout, dlow, C1, C2, H, up_ratio(H), up_ratio(W));
+        else upcat_bwd_low_tiled_kernel<1><<<grid, 256, 0, st>>>(dout, dlow, C1, C2, H, up_ratio(H), up_ratio(W));
         SIFNN_TRY(sifnn::check_launch("upcat_bwd_low_tiled_kernel"));
     } else {
         upcat_bwd_low_kernel<<<grid_for(total, 256), 256, 0, st>>>(dout, dlow, total, C1, C2, H, W, up_ratio(H), up_ratio(W));
