@@ -233,6 +233,76 @@ __global__ void __launch_bounds__(256) act_upcat_kernel(const float* __restrict_
     *reinterpret_cast<float4*>(out + ((size_t)b * (C1 + C2) + c) * Ho * Wo + (size_t)y * Wo + x) = v;
 }
 
+// Same operation for C1 == C2, C1 % 4 == 0 (every decoder level).  act_upcat_kernel is bound by instruction issue on its up-sampled
+// half (ncu: 82 % issue active, ~375 instructions per thread, most of them source coordinates and 64-bit addresses) while its skip
+// half is a pure copy.  Here a thread owns four output pixels of UPC = 4 up-sampled channels AND of 4 skip channels: coordinates and
+// source offsets are computed once, the skip loads are issued first and the gathers of channel u + 1 before channel u is
+// interpolated, so every warp carries both kinds of work and the copy's latency hides behind the interpolation.
+// grid = (ceil(Ho*Wo/4 / 256), C1/4, B).
+constexpr int UPC = 4;
+__global__ void __launch_bounds__(256, 2) act_upcat4_kernel(const float* __restrict__ low, const float* __restrict__ lsc, const float* __restrict__ lsh,
+                                                            const float* __restrict__ skip, const float* __restrict__ ssc, const float* __restrict__ ssh,
+                                                            float* __restrict__ out, int C1, int H, int W, float ry, float rx) {
+    const int Ho = 2 * H, Wo = 2 * W, Wq = Wo >> 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Ho * Wq) return;
+    const int y = t / Wq, x = (t - y * Wq) * 4;
+    const int b = blockIdx.z;
+    const size_t oplane = (size_t)Ho * Wo;
+    const int ooff = y * Wo + x;
+    const int c0 = blockIdx.y * UPC;
+    float4 s4[UPC];
+    {
+        const float* sp = skip + ((size_t)b * C1 + c0) * oplane + ooff;
+#pragma unroll
+        for (int u = 0; u < UPC; ++u) s4[u] = __ldg(reinterpret_cast<const float4*>(sp + u * oplane));
+    }
+    const UpCoord uy = up_coord(y, H, ry);
+    int o0[4], o1[4];
+    float wx0[4], wx1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const UpCoord ux = up_coord(x + j, W, rx);
+        o0[j] = ux.i0; o1[j] = ux.i1;
+        wx0[j] = ux.w0; wx1[j] = ux.w1;
+    }
+    const float* p0 = low + ((size_t)b * C1 + c0) * H * W + uy.i0 * W;
+    const float* p1 = low + ((size_t)b * C1 + c0) * H * W + uy.i1 * W;
+    float* q = out + ((size_t)b * 2 * C1 + c0) * oplane + ooff;
+    float* qs = q + (size_t)C1 * oplane;
+    float v[4][4], n[4][4];
+    auto fetch = [&](float (&d)[4][4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            d[j][0] = __ldg(p0 + o0[j]); d[j][1] = __ldg(p0 + o1[j]);
+            d[j][2] = __ldg(p1 + o0[j]); d[j][3] = __ldg(p1 + o1[j]);
+        }
+        p0 += (size_t)H * W; p1 += (size_t)H * W;
+    };
+    fetch(n);
+#pragma unroll
+    for (int u = 0; u < UPC; ++u) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[j][e] = n[j][e];
+        if (u + 1 < UPC) fetch(n);
+        const float sc = __ldg(lsc + c0 + u), sh = __ldg(lsh + c0 + u);
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float v00 = sifnn::act_affine_relu(v[j][0], sc, sh), v01 = sifnn::act_affine_relu(v[j][1], sc, sh);
+            const float v10 = sifnn::act_affine_relu(v[j][2], sc, sh), v11 = sifnn::act_affine_relu(v[j][3], sc, sh);
+            r[j] = uy.w0 * (wx0[j] * v00 + wx1[j] * v01) + uy.w1 * (wx0[j] * v10 + wx1[j] * v11);
+        }
+        *reinterpret_cast<float4*>(q + u * oplane) = make_float4(r[0], r[1], r[2], r[3]);
+        const float k_sc = __ldg(ssc + c0 + u), k_sh = __ldg(ssh + c0 + u);
+        *reinterpret_cast<float4*>(qs + u * oplane) =
+            make_float4(sifnn::act_affine_relu(s4[u].x, k_sc, k_sh), sifnn::act_affine_relu(s4[u].y, k_sc, k_sh),
+                        sifnn::act_affine_relu(s4[u].z, k_sc, k_sh), sifnn::act_affine_relu(s4[u].w, k_sc, k_sh));
+    }
+}
+
 // dlow[b][c][i][k] = sum_{y,x} wy(i,y) wx(k,x) dout[b][c][y][x]  (gather form of the adjoint)
 __global__ void __launch_bounds__(256) upcat_bwd_low_kernel(const float* __restrict__ dout, float* __restrict__ dlow, long long total,
                                                             int C1, int C2, int H, int W, float ry, float rx) {
@@ -505,6 +575,12 @@ extern "C" int sifnn_act_upcat_fwd(const float* low, const float* low_scale, con
     SIFNN_REQUIRE(low && low_scale && low_shift && skip && skip_scale && skip_shift && out, "act_upcat_fwd: null pointer");
     SIFNN_REQUIRE(B > 0 && C1 > 0 && C2 > 0 && H > 0 && W > 0, "act_upcat_fwd: bad shape");
     SIFNN_REQUIRE(W % 2 == 0 && B <= 65535 && C1 + C2 <= 65535, "act_upcat_fwd: need even W, B and channels <= 65535");
+    if (C1 == C2 && C1 % UPC == 0) {
+        dim3 grid4((2 * H * (2 * W / 4) + 255) / 256, C1 / UPC, B);
+        act_upcat4_kernel<<<grid4, 256, 0, sifnn::as_stream(stream)>>>(low, low_scale, low_shift, skip, skip_scale, skip_shift, out, C1, H, W,
+                                                                        up_ratio(H), up_ratio(W));
+        return sifnn::check_launch("act_upcat4_kernel");
+    }
     dim3 grid((2 * H * (2 * W / 4) + 255) / 256, C1 + C2, B);
     act_upcat_kernel<<<grid, 256, 0, sifnn::as_stream(stream)>>>(low, low_scale, low_shift, skip, skip_scale, skip_shift, out, C1, C2, H, W,
                                                                    up_ratio(H), up_ratio(W));

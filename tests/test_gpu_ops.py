@@ -240,3 +240,18 @@ def test_single_output_channel_layer(shape):
     wr2 = w.double().clone().requires_grad_(True)
     (ref_conv(x, wr2) * dy.double()).sum().backward()
     assert rel_err(dw2, wr2.grad) < TOL
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 32, 32), (1, 4, 4, 5, 6), (3, 8, 8, 17, 34), (1, 32, 32, 8, 8), (2, 4, 8, 9, 10), (1, 6, 6, 7, 8), (2, 3, 5, 4, 4)])
+def test_act_upcat_shapes(shape):
+    """BatchNorm + ReLU + bilinear x2 (align_corners=True) + concat: the fused 4 + 4 channel kernel (C1 == C2, C1 % 4 == 0) and the
+    generic one, odd heights, widths that leave a partial last CTA."""
+    B, C1, C2, H, W = shape
+    low, skip = rnd(B, C1, H, W, seed=81), rnd(B, C2, 2 * H, 2 * W, seed=82)
+    s1, h1 = 1 + 0.3 * rnd(C1, seed=83), 0.2 * rnd(C1, seed=84)
+    s2, h2 = 1 + 0.3 * rnd(C2, seed=85), 0.2 * rnd(C2, seed=86)
+    u = ops.act_upcat_fwd(low.cuda(), s1.cuda(), h1.cuda(), skip.cuda(), s2.cuda(), h2.cuda())
+    act = F.relu(low * s1[None, :, None, None] + h1[None, :, None, None])
+    ref = torch.cat([F.interpolate(act, scale_factor=2, mode="bilinear", align_corners=True),
+                     F.relu(skip * s2[None, :, None, None] + h2[None, :, None, None])], 1)
+    assert u.shape == ref.shape and rel_err(u, ref) < 2e-6
