@@ -373,8 +373,8 @@ __device__ __forceinline__ void up_gather_weights(int i, int n_in, float r, floa
     }
 }
 template <int LR>
-__global__ void __launch_bounds__(256) upcat_bwd_low_tiled_kernel(const float* __restrict__ dout, float* __restrict__ dlow, int C1, int C2, int H,
-                                                                  float ry, float rx) {
+__global__ void __launch_bounds__(256) upcat_bwd_low_tiled_kernel(const float* __restrict__ dout, float* __restrict__ dlow, float* __restrict__ dskip,
+                                                                  int C1, int C2, int H, float ry, float rx) {
     constexpr int W = 32 * LR, Wo = 2 * W, Wq = Wo / 4, STRIDE = Wo + 8;   // staged row: column x at index x + 4, zeros at -2, -1, Wo, Wo + 1
     __shared__ __align__(16) float in_s[UPB_NR * STRIDE];
     __shared__ float wy_s[UPB_TL][6];      // the y weights depend on the row only: one thread per low-resolution row computes them once
@@ -385,6 +385,18 @@ __global__ void __launch_bounds__(256) upcat_bwd_low_tiled_kernel(const float* _
     const int i_lo = blockIdx.x * UPB_TL;
     const int y_lo = 2 * i_lo - 2;
     const float* g = dout + ((size_t)b * (C1 + C2) + c) * Ho * Wo;
+    // C1 == C2 (dskip != nullptr): this CTA also copies the band's 16 output rows of skip channel c, LR 16-byte pieces per thread; the
+    // loads are issued here and stored at the end, so the copy's latency hides behind the adjoint (it was a launch of its own)
+    float4 sk[LR];
+    if (dskip) {
+        const float* gs = dout + ((size_t)b * (C1 + C2) + C1 + c) * Ho * Wo;
+#pragma unroll
+        for (int u = 0; u < LR; ++u) {
+            const int idx = tid + u * 256, r = idx / Wq, x4 = idx % Wq;
+            const int y = 2 * i_lo + r;
+            sk[u] = y < Ho ? __ldg(reinterpret_cast<const float4*>(gs + (size_t)y * Wo) + x4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
 #pragma unroll
     for (int idx = tid; idx < UPB_NR * Wq; idx += 256) {
         const int r = idx / Wq, x4 = idx % Wq;
@@ -422,6 +434,15 @@ __global__ void __launch_bounds__(256) upcat_bwd_low_tiled_kernel(const float* _
 #pragma unroll
             for (int t = 0; t < 6; ++t) acc = fmaf(wy_s[il0 + l][t], xr[2 * l + t], acc);
             dlow[((size_t)plane * H + i) * W + k] = acc;
+        }
+    }
+    if (dskip) {
+        float* ds = dskip + ((size_t)b * C2 + c) * Ho * Wo;
+#pragma unroll
+        for (int u = 0; u < LR; ++u) {
+            const int idx = tid + u * 256, r = idx / Wq, x4 = idx % Wq;
+            const int y = 2 * i_lo + r;
+            if (y < Ho) *(reinterpret_cast<float4*>(ds + (size_t)y * Wo) + x4) = sk[u];
         }
     }
 }
@@ -594,9 +615,11 @@ extern "C" int sifnn_upcat_bwd(const float* dout, float* dlow, float* dskip, int
     const long long total = (long long)B * C1 * H * W;
     if ((W == 32 || W == 64 || W == 128) && (long long)B * C1 <= 65535) {
         dim3 grid((H + UPB_TL - 1) / UPB_TL, B * C1);
-        if (W == 128) upcat_bwd_low_tiled_kernel<4><<<grid, 256, 0, st>>>(dout, dlow, C1, C2, H, up_ratio(H), up_ratio(W));
-        else if (W == 64) upcat_bwd_low_tiled_kernel<2><<<grid, 256, 0, st>>>(dout, dlow, C1, C2, H, up_ratio(H), up_ratio(W));
-        else upcat_bwd_low_tiled_kernel<1><<<grid, 256, 0, st>>>(dout, dlow, C1, C2, H, up_ratio(H), up_ratio(W));
+        float* fused_skip = (C1 == C2) ? dskip : nullptr;
+        if (W == 128) upcat_bwd_low_tiled_kernel<4><<<grid, 256, 0, st>>>(dout, dlow, fused_skip, C1, C2, H, up_ratio(H), up_ratio(W));
+        else if (W == 64) upcat_bwd_low_tiled_kernel<2><<<grid, 256, 0, st>>>(dout, dlow, fused_skip, C1, C2, H, up_ratio(H), up_ratio(W));
+        else upcat_bwd_low_tiled_kernel<1><<<grid, 256, 0, st>>>(dout, dlow, fused_skip, C1, C2, H, up_ratio(H), up_ratio(W));
+        if (fused_skip) return sifnn::check_launch("upcat_bwd_low_tiled_kernel");
         SIFNN_TRY(sifnn::check_launch("upcat_bwd_low_tiled_kernel"));
     } else {
         upcat_bwd_low_kernel<<<grid_for(total, 256), 256, 0, st>>>(dout, dlow, total, C1, C2, H, W, up_ratio(H), up_ratio(W));

@@ -165,16 +165,17 @@ def test_pool_residual_upcat():
     assert torch.equal(dskip.cpu(), go[:, C:])
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 32, 32), (1, 8, 64, 64), (2, 4, 128, 128), (1, 3, 20, 128), (2, 5, 12, 24), (1, 2, 8, 8)])
+@pytest.mark.parametrize("shape", [(2, 16, 32, 32), (1, 8, 64, 64), (2, 4, 128, 128), (1, 3, 20, 128), (2, 5, 12, 24), (1, 2, 8, 8), (1, 2, 13, 32), (2, 3, 9, 64)])
 def test_upcat_bwd_shapes(shape):
     """Adjoint of the bilinear x2 (align_corners=True) up-sampling: tiled kernel (power-of-two widths <= 128) and the generic one."""
     B, C, H, W = shape
-    go = rnd(B, C + 3, 2 * H, 2 * W, seed=61)
-    lo = torch.zeros(B, C, H, W, dtype=torch.float64, requires_grad=True)
-    (F.interpolate(lo, scale_factor=2, mode="bilinear", align_corners=True) * go[:, :C].double()).sum().backward()
-    dlow, dskip = ops.upcat_bwd(go.cuda(), C)
-    assert rel_err(dlow, lo.grad) < 1e-5
-    assert torch.equal(dskip.cpu(), go[:, C:])
+    for C2 in (3, C):            # C2 == C: the tiled kernel also copies the skip half (no second launch)
+        go = rnd(B, C + C2, 2 * H, 2 * W, seed=61)
+        lo = torch.zeros(B, C, H, W, dtype=torch.float64, requires_grad=True)
+        (F.interpolate(lo, scale_factor=2, mode="bilinear", align_corners=True) * go[:, :C].double()).sum().backward()
+        dlow, dskip = ops.upcat_bwd(go.cuda(), C)
+        assert rel_err(dlow, lo.grad) < 1e-5
+        assert torch.equal(dskip.cpu(), go[:, C:])
 
 
 def test_bicubic4_cat_matches_cv2_golden(golden):
