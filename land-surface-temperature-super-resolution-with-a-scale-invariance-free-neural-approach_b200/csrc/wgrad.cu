@@ -338,24 +338,24 @@ __global__ void __launch_bounds__((O_CHUNK / OT) * (K_CHUNK / KT) * 32, 1) wgrad
     }
 }
 
-// out[i] = sum_s partial[s][i] in a fixed order (deterministic): 8 slice-strided sums per output, combined in order.  Outputs
+// out[i] = sum_s partial[s][i] in a fixed order (deterministic): 32 slice-strided sums per output, combined in order.  Outputs
 // n .. n + nb - 1 are the bias gradient (own partial array), so one launch finishes both.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int S,
+__global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int S,
                                                            const float* __restrict__ bias_partial, float* __restrict__ bias_out, int nb) {
-    __shared__ float red[8][33];
+    __shared__ float red[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + tx;
     const float* src = i < n ? partial + i : bias_partial + (i - n);
     const int stride = i < n ? n : nb;
     float acc = 0.f;
     if (i < n + nb)
-        for (int s = ty; s < S; s += 8) acc += __ldg(src + (size_t)s * stride);
+        for (int s = ty; s < S; s += 32) acc += __ldg(src + (size_t)s * stride);
     red[ty][tx] = acc;
     __syncthreads();
     if (ty == 0 && i < n + nb) {
         float t = red[0][tx];
 #pragma unroll
-        for (int j = 1; j < 8; ++j) t += red[j][tx];
+        for (int j = 1; j < 32; ++j) t += red[j][tx];
         if (i < n) out[i] = t;
         else bias_out[i - n] = t;
     }
@@ -544,7 +544,7 @@ extern "C" int sifnn_conv3x3_wgrad(const float* in, const float* in_scale, const
     else SIFNN_TRY((launch_wgrad<4, 2, 16, 8, false>(a, p, affine, st)));
     const int n = Cout * Cin * 9;
     const int nb = dbias ? Cout : 0;
-    wgrad_reduce_kernel<<<(n + nb + 31) / 32, 256, 0, st>>>(a.partial, dw, n, S, a.bias_partial, dbias, nb);
+    wgrad_reduce_kernel<<<(n + nb + 31) / 32, 1024, 0, st>>>(a.partial, dw, n, S, a.bias_partial, dbias, nb);
     SIFNN_TRY(sifnn::check_launch("wgrad_reduce_kernel"));
     return 0;
 }

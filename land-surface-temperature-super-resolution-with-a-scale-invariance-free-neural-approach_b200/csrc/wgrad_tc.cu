@@ -346,20 +346,20 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) wgrad_tc_kernel(const WtcArgs 
     }
 }
 
-// out[i] = sum_s partial[s][i], fixed summation order (deterministic): 8 slice-strided partial sums per output, combined in order.
-__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int S) {
-    __shared__ float red[8][33];
+// out[i] = sum_s partial[s][i], fixed summation order (deterministic): 32 slice-strided partial sums per output, combined in order.
+__global__ void __launch_bounds__(1024) wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int S) {
+    __shared__ float red[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + tx;
     float acc = 0.f;
     if (i < n)
-        for (int s = ty; s < S; s += 8) acc += __ldg(partial + (size_t)s * n + i);
+        for (int s = ty; s < S; s += 32) acc += __ldg(partial + (size_t)s * n + i);
     red[ty][tx] = acc;
     __syncthreads();
     if (ty == 0 && i < n) {
         float t = red[0][tx];
 #pragma unroll
-        for (int j = 1; j < 8; ++j) t += red[j][tx];
+        for (int j = 1; j < 32; ++j) t += red[j][tx];
         out[i] = t;
     }
 }
@@ -438,6 +438,6 @@ extern "C" int sifnn_conv3x3_wgrad_tc(const float* in, const float* in_scale, co
     }
     SIFNN_TRY(rc);
     const int n = Cout * Cin * 9;
-    wgrad_tc_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(a.partial, dw, n, S);
+    wgrad_tc_reduce_kernel<<<(n + 31) / 32, 1024, 0, st>>>(a.partial, dw, n, S);
     return sifnn::check_launch("wgrad_tc_reduce_kernel");
 }
