@@ -420,13 +420,19 @@ class PinnedBatchLoader:
     just had, and the slot is handed back to the workers only after that event has completed, so asynchronous copies out of
     the slot (``.to(device, non_blocking=True)``, ``step_host_async``) issued before the next ``next()`` are safe.
     Iteration order follows ``torch.randperm`` with ``seed + epoch`` (or the global generator when seed is None), like
-    DataLoader(shuffle=True); the last short batch is kept unless ``drop_last``.  ``close()`` stops the workers."""
+    DataLoader(shuffle=True); the last short batch is kept unless ``drop_last``.  ``rank`` / ``world_size`` shard every epoch's
+    permutation over the data-parallel ranks like DistributedSampler (same seed on every rank).  ``close()`` stops the workers."""
 
     def __init__(self, dataset, batch_size: int, shuffle: bool = True, seed: Optional[int] = None, drop_last: bool = False,
                  workers: int = 1, depth: int = 3, with_upsampled: bool = True, pin: Optional[bool] = None,
-                 processes: bool = False, chunk: int = 8):
+                 processes: bool = False, chunk: int = 8, rank: int = 0, world_size: int = 1):
         if batch_size < 1 or depth < 2 or workers < 1 or chunk < 1:
             raise SifnnError("PinnedBatchLoader: batch_size >= 1, depth >= 2, workers >= 1, chunk >= 1")
+        if world_size < 1 or not 0 <= rank < world_size:
+            raise SifnnError("PinnedBatchLoader: need 0 <= rank < world_size")
+        if world_size > 1 and shuffle and seed is None:
+            raise SifnnError("PinnedBatchLoader: data-parallel shuffling needs a seed (every rank must draw the same permutation)")
+        self.rank, self.world_size = rank, world_size
         self.dataset, self.batch_size, self.shuffle, self.seed, self.drop_last = dataset, batch_size, shuffle, seed, drop_last
         self.workers, self.depth, self.with_upsampled = workers, depth, with_upsampled
         self.processes, self.chunk = processes, chunk
@@ -438,8 +444,11 @@ class PinnedBatchLoader:
         self._registered: List[int] = []
         self._active: Optional["_LoaderIter"] = None
 
+    def _shard_len(self):
+        return (len(self.dataset) + self.world_size - 1) // self.world_size
+
     def __len__(self):
-        n = len(self.dataset)
+        n = self._shard_len()
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
     # -- buffers and workers, created at the first iteration
@@ -517,6 +526,12 @@ class PinnedBatchLoader:
         else:
             order = list(range(n))
         self.epoch += 1
+        if self.world_size > 1:
+            # torch.utils.data.DistributedSampler semantics: the permutation is padded by wrapping around to a multiple of the
+            # world size and dealt out round-robin, so every rank gets the same number of samples (equal step counts)
+            pad = self._shard_len() * self.world_size - n
+            order = (order + order[:pad])[self.rank::self.world_size] if n else []
+            n = len(order)
         batches = [order[i:i + self.batch_size] for i in range(0, n, self.batch_size)]
         if self.drop_last and batches and len(batches[-1]) < self.batch_size:
             batches.pop()

@@ -313,3 +313,31 @@ def test_loader_process_workers(tmp_path):
         a.close()
         b.close()
     assert not b._pool
+
+
+def test_loader_rank_sharding(tmp_path):
+    """Data-parallel sharding: the ranks' epochs partition one common permutation (padded by wrap-around to equal lengths)."""
+    csv, stats = _make_dataset(tmp_path)
+    d = ds.ModisDatasetB(csv, stats_path=stats)           # 9 samples
+    items = [d[i][0] for i in range(len(d))]
+
+    def ids(loader):
+        out = []
+        for lst, _, _ in loader:
+            for j in range(lst.shape[0]):
+                out.append(next(i for i, it in enumerate(items) if np.array_equal(it, lst[j].numpy())))
+        return out
+    world = 2
+    per_rank = [ids(ds.PinnedBatchLoader(d, 2, shuffle=True, seed=4, with_upsampled=False, pin=False, rank=r, world_size=world)) for r in range(world)]
+    g = torch.Generator(); g.manual_seed(4)
+    perm = torch.randperm(9, generator=g).tolist()
+    padded = perm + perm[:1]
+    assert per_rank[0] == padded[0::2] and per_rank[1] == padded[1::2]
+    assert len(per_rank[0]) == len(per_rank[1]) == 5
+    assert len(ds.PinnedBatchLoader(d, 2, seed=4, pin=False, rank=1, world_size=2)) == 3
+    seq = [ids(ds.PinnedBatchLoader(d, 4, shuffle=False, with_upsampled=False, pin=False, rank=r, world_size=3)) for r in range(3)]
+    assert seq == [[0, 3, 6], [1, 4, 7], [2, 5, 8]]
+    with pytest.raises(SifnnError, match="seed"):
+        ds.PinnedBatchLoader(d, 2, shuffle=True, rank=0, world_size=2)
+    with pytest.raises(SifnnError, match="rank"):
+        ds.PinnedBatchLoader(d, 2, seed=1, rank=2, world_size=2)
