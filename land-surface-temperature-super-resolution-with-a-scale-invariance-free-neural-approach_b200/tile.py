@@ -55,3 +55,18 @@ def super_resolve_tile(model: ModelB_2, lst_tile: torch.Tensor, ndvi_tile: torch
         sr = model.forward_from_lowres(lst, ndvi)
         _lib.call("sifnn_tile_scatter", sr.data_ptr(), wy[i:].data_ptr(), wx[i:].data_ptr(), out.data_ptr(), p, ht, wt, ml, sl, _stream())
     return out
+
+
+def super_resolve_geotiff(model: ModelB_2, lst_file, ndvi_file, out_file, stats: Dict[str, float], batch: int = 64,
+                          device: Optional[torch.device] = None) -> torch.Tensor:
+    """File-to-file form of predict.py:70-125 for rasters that are already GeoTiffs: LST in Kelvin at (Ht, Wt), NDVI at (4Ht, 4Wt).
+    Reads both with the GDAL-free reader, runs ``super_resolve_tile`` and writes ``out_file`` on the NDVI grid (the reference saves
+    its prediction with the CRS and transform of the 250 m product, predict.py:104-125).  Returns the LST_SR tile (device tensor).
+    The HDF side of predict.py (us.read_LST / read_NIRRED / compute_NDVI) is outside this library: no HDF4 reader here."""
+    from .dataset import read_geotiff, save_geotiff
+    lst, _, _, _, _ = read_geotiff(lst_file)
+    ndvi, _, _, projection, geotransform = read_geotiff(ndvi_file)
+    dev = device or next(model.parameters()).device
+    out = super_resolve_tile(model, torch.from_numpy(lst).to(dev), torch.from_numpy(ndvi).to(dev), stats, batch=batch)
+    save_geotiff(out.cpu().numpy(), out_file, projection, geotransform)
+    return out

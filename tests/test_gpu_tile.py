@@ -74,3 +74,22 @@ def test_pipelined_inference_matches_direct_forward():
             assert torch.equal(m.forward_from_lowres(l.cuda(), n.cuda()).cpu(), o)
     with pytest.raises(sifnn_b200.SifnnError):
         pipe.submit(batches[0][0].clone(), batches[0][1], outs[0])   # not pinned
+
+
+def test_tile_from_geotiff_files(tmp_path):
+    """File-to-file driver: GeoTiff in, GeoTiff out on the NDVI grid, same pixels as the in-memory tile driver."""
+    sd = load_ckpt("1009")
+    m = model_mod.ModelB_2(2)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    lst, ndvi = make_tile(ht=64, wt=132, seed=5)
+    gt_lst, gt_ndvi = (500000.0, 1000.0, 0.0, 4600000.0, 0.0, -1000.0), (500000.0, 250.0, 0.0, 4600000.0, 0.0, -250.0)
+    fl, fn, fo = tmp_path / "lst.tif", tmp_path / "ndvi.tif", tmp_path / "prediction.tif"
+    sifnn_b200.save_geotiff(lst.numpy(), fl, "EPSG:32631", gt_lst)
+    sifnn_b200.save_geotiff(ndvi.numpy(), fn, "EPSG:32631", gt_ndvi)
+    out = sifnn_b200.super_resolve_geotiff(m, fl, fn, fo, STATS, batch=2)
+    ref = sifnn_b200.super_resolve_tile(m, lst.cuda(), ndvi.cuda(), STATS, batch=2)
+    assert torch.equal(out, ref) and float(out[:, :4 * 128].abs().min()) > 0.0
+    img, cols, rows, proj, gt = sifnn_b200.read_geotiff(fo)
+    assert (rows, cols) == tuple(ndvi.shape) and proj == "EPSG:32631" and gt == gt_ndvi
+    assert np.array_equal(img, ref.cpu().numpy())
