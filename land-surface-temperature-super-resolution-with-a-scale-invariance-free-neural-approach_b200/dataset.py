@@ -421,11 +421,12 @@ class PinnedBatchLoader:
     the slot (``.to(device, non_blocking=True)``, ``step_host_async``) issued before the next ``next()`` are safe.
     Iteration order follows ``torch.randperm`` with ``seed + epoch`` (or the global generator when seed is None), like
     DataLoader(shuffle=True); the last short batch is kept unless ``drop_last``.  ``rank`` / ``world_size`` shard every epoch's
-    permutation over the data-parallel ranks like DistributedSampler (same seed on every rank).  ``close()`` stops the workers."""
+    permutation over the data-parallel ranks like DistributedSampler (same seed on every rank).  ``close()`` stops the workers;
+    a consumer that sees no finished work item for ``stall_timeout`` seconds raises instead of waiting forever."""
 
     def __init__(self, dataset, batch_size: int, shuffle: bool = True, seed: Optional[int] = None, drop_last: bool = False,
                  workers: int = 1, depth: int = 3, with_upsampled: bool = True, pin: Optional[bool] = None,
-                 processes: bool = False, chunk: int = 8, rank: int = 0, world_size: int = 1):
+                 processes: bool = False, chunk: int = 8, rank: int = 0, world_size: int = 1, stall_timeout: float = 300.0):
         if batch_size < 1 or depth < 2 or workers < 1 or chunk < 1:
             raise SifnnError("PinnedBatchLoader: batch_size >= 1, depth >= 2, workers >= 1, chunk >= 1")
         if world_size < 1 or not 0 <= rank < world_size:
@@ -433,6 +434,7 @@ class PinnedBatchLoader:
         if world_size > 1 and shuffle and seed is None:
             raise SifnnError("PinnedBatchLoader: data-parallel shuffling needs a seed (every rank must draw the same permutation)")
         self.rank, self.world_size = rank, world_size
+        self.stall_timeout = stall_timeout    # seconds without any finished work item before the consumer gives up (a hung worker)
         self.dataset, self.batch_size, self.shuffle, self.seed, self.drop_last = dataset, batch_size, shuffle, seed, drop_last
         self.workers, self.depth, self.with_upsampled = workers, depth, with_upsampled
         self.processes, self.chunk = processes, chunk
@@ -571,12 +573,19 @@ class _LoaderIter:
                 self.outstanding += 1
 
     def _collect_one(self):
+        waited = 0.0
         while True:
             try:
                 gen, b, n, err = self.l._done.get(timeout=1.0)
             except queue.Empty:
                 if not all(p.is_alive() for p in self.l._pool):
                     raise SifnnError("PinnedBatchLoader: a worker died")
+                waited += 1.0
+                if waited >= self.l.stall_timeout:
+                    if self.l.processes:
+                        for p in self.l._pool:
+                            p.terminate()
+                    raise SifnnError(f"PinnedBatchLoader: no work item finished for {self.l.stall_timeout:.0f} s (worker stalled)")
                 continue
             if gen != self.gen:
                 continue

@@ -341,3 +341,25 @@ def test_loader_rank_sharding(tmp_path):
         ds.PinnedBatchLoader(d, 2, shuffle=True, rank=0, world_size=2)
     with pytest.raises(SifnnError, match="rank"):
         ds.PinnedBatchLoader(d, 2, seed=1, rank=2, world_size=2)
+
+
+def test_loader_stall_timeout(tmp_path):
+    """A worker that never finishes must not hang the consumer."""
+    import time
+    csv, stats = _make_dataset(tmp_path)
+    d = ds.ModisDatasetB(csv, stats_path=stats)
+
+    class Slow:
+        def __len__(self):
+            return len(d)
+
+        def load_pair(self, idx, lst_out=None, ndvi_out=None):
+            if lst_out is not None and idx == 3:
+                time.sleep(6.0)
+            return d.load_pair(idx, lst_out, ndvi_out)
+    ld = ds.PinnedBatchLoader(Slow(), 4, shuffle=False, workers=1, pin=False, with_upsampled=False, stall_timeout=2.0)
+    t0 = time.time()
+    with pytest.raises(SifnnError, match="stalled"):
+        for _ in ld:
+            pass
+    assert time.time() - t0 < 5.5
