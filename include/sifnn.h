@@ -74,6 +74,24 @@ int sifnn_conv3x3_dgrad_tc(const float* dy, const float* w, float* dx, int accum
 int sifnn_conv3x3_dgrad_border(const float* dy, const float* w, float* dx,
                                int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
 
+/* Full-fold tensor-core convolution (csrc/conv3x3_ff.cu, round 2): the nine taps of 16 output channels are one N = 144 MMA per 16 (BF16 split)
+ * or 8 (TF32 split, SIFNN_FF_TF32=1) input channels; the epilogue shifts and adds.  Same semantics as sifnn_conv3x3_fwd (no bias) and as the COMPLETE
+ * sifnn_conv3x3_dgrad (the adjoint of the replicate padding is part of the epilogue: no border pass).  Shapes: W in {32,64,128,256},
+ * Cin (forward) / Cout (data gradient) a multiple of 16 up to 64, the other channel count a multiple of 16 up to 128.
+ * wprep: sifnn_conv3x3_tc_wprep_bytes() bytes of scratch. */
+int sifnn_conv3x3_ff_supported(int Cin, int Cout, int H, int W);
+/* tf32 != 0: TF32 split instead of BF16; max_ctas > 0 caps gridDim.x (tests: long row strips on small inputs), 0 = one CTA per SM */
+void sifnn_conv3x3_ff_config(int tf32, int max_ctas);
+/* debug: ablation bits for pipeline studies (1 no MMAs, 2 no epilogue math, 4 no TMEM loads, 8 no transform, 16 no stores, 32 L2-resident loads); results are then wrong */
+void sifnn_conv3x3_ff_debug(int ablate);
+/* debug: device buffer of 11 * 256 uint64 that receives clock64 stamps of CTA (0,0) per pipeline step (tools/trace_ff.py), or NULL */
+void sifnn_conv3x3_ff_trace(void* buf);
+int sifnn_conv3x3_fwd_ff(const float* in, const float* in_scale, const float* in_shift, const float* w,
+                         float* out, double* stats, void* wprep,
+                         int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+int sifnn_conv3x3_dgrad_ff(const float* dy, const float* w, float* dx, int accumulate, void* wprep,
+                           int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+
 /* Weight gradient.  `in`/in_scale/in_shift as in sifnn_conv3x3_fwd.  dw (Cout,Cin,3,3)
  * is overwritten; dbias (Cout) or NULL.  workspace: sifnn_conv3x3_wgrad_workspace()
  * bytes of scratch (per-CTA partial sums, reduced in a fixed order -> deterministic). */

@@ -23,6 +23,13 @@ int conv3x3_fwd_tc_prepped(const float* in, const float* in_scale, const float* 
 int conv3x3_dgrad_tc_main_prepped(const float* dy, const void* wprep, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
 int conv3x3_dgrad_border_cols(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
 
+// Full-fold tensor-core convolution (csrc/conv3x3_ff.cu): all nine taps in the MMA's N dimension, shift-and-add epilogue, padding adjoint included.
+bool conv3x3_ff_supported(int K, int O, int H, int W);
+int ff_prep(const float* const* w, void* const* wprep, const int* K, const int* O, const int* w_so, const int* w_sk, const int* flip, int n, cudaStream_t st);
+int conv3x3_fwd_ff_prepped(const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, float* out, double* stats,
+                           int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
+int conv3x3_dgrad_ff_prepped(const float* dy, const void* wprep, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
+
 inline cudaStream_t as_stream(sifnn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -18,21 +18,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Two ways to wait on an mbarrier phase.  tools/load_probe2.cu (profiles/r2e_load_probe2.log): a thread parked in mbarrier.try_wait is
+// resumed 450-900 clocks AFTER the phase completes (12 TMA boxes that landed at clock ~970 are seen at ~1450 and later); a test_wait spin
+// sees the completion within ~70 clocks but takes issue slots from the working warps of its scheduler (the full-fold convolution got 14 %
+// slower with every role spinning).  So: mbar_wait (suspending) for the roles that run ahead, mbar_wait_spin for the one wait on the
+// critical path of a kernel.  -DSIFNN_MBAR_HINT=<ns> gives the suspending form a time hint (A/B builds).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#ifdef SIFNN_MBAR_TEST_WAIT
-    // pure spin on the non-blocking test_wait (no hardware suspend between polls)
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-#elif defined(SIFNN_MBAR_HINT)
+#if defined(SIFNN_MBAR_HINT)
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -57,6 +49,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 #endif
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 // warp-collective wait: one lane polls, the others park at the warp barrier (32x less polling traffic on the barrier word)
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {

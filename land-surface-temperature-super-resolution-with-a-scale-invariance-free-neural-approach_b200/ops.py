@@ -81,6 +81,32 @@ def conv3x3_dgrad_tc(dy, w, dx: Optional[torch.Tensor] = None, accumulate: bool 
     return dx
 
 
+def conv3x3_fwd_ff(x, w, in_scale=None, in_shift=None, stats: Optional[torch.Tensor] = None):
+    """Full-fold tcgen05 forward (csrc/conv3x3_ff.cu): nine taps per MMA, shift-and-add epilogue."""
+    _chk(x, w, in_scale, in_shift, stats)
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    lib = _lib.load()
+    wprep = torch.empty(lib.sifnn_conv3x3_tc_wprep_bytes(Cin, Cout), dtype=torch.uint8, device=x.device)
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device)
+    _lib.call("sifnn_conv3x3_fwd_ff", _p(x), _p(in_scale), _p(in_shift), _p(w), _p(out), _p(stats), _p(wprep), B, Cin, Cout, H, W, _s())
+    return out
+
+
+def conv3x3_dgrad_ff(dy, w, dx: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """Full-fold tcgen05 data gradient, padding adjoint included (one launch)."""
+    _chk(dy, w, dx)
+    B, Cout, H, W = dy.shape
+    Cin = w.shape[1]
+    lib = _lib.load()
+    wprep = torch.empty(lib.sifnn_conv3x3_tc_wprep_bytes(Cout, Cin), dtype=torch.uint8, device=dy.device)
+    if dx is None:
+        dx = torch.empty((B, Cin, H, W), dtype=torch.float32, device=dy.device)
+        accumulate = False
+    _lib.call("sifnn_conv3x3_dgrad_ff", _p(dy), _p(w), _p(dx), 1 if accumulate else 0, _p(wprep), B, Cin, Cout, H, W, _s())
+    return dx
+
+
 def conv3x3_wgrad(x, dy, in_scale=None, in_shift=None, want_bias: bool = False):
     _chk(x, dy, in_scale, in_shift)
     B, Cin, H, W = x.shape
