@@ -92,6 +92,20 @@ int sifnn_conv3x3_fwd_ff(const float* in, const float* in_scale, const float* in
 int sifnn_conv3x3_dgrad_ff(const float* dy, const float* w, float* dx, int accumulate, void* wprep,
                            int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
 
+/* Fold + shift tensor-core convolution (csrc/conv3x3_fs.cu, round 2) for widths that are multiples of 128: the three filter rows are stacked in the MMA's
+ * N dimension, the three filter columns are three start addresses into one staged input row, the epilogue keeps two partial output rows in registers.
+ * Same semantics as sifnn_conv3x3_fwd (no bias) and the COMPLETE sifnn_conv3x3_dgrad.  Channel limits as for the full-fold kernel.
+ * wprep: sifnn_conv3x3_tc_wprep_bytes() bytes; the data gradient needs 2 * Cout * 3 * Cin * 4 bytes more (fp32 edge taps). */
+int sifnn_conv3x3_fs_supported(int Cin, int Cout, int H, int W);
+void sifnn_conv3x3_fs_config(int tf32, int max_ctas);
+/* debug: device buffer of 16 * 256 uint64 for clock64 stamps of CTA (0,0) per pipeline step (tools/trace_fs.py), or NULL */
+void sifnn_conv3x3_fs_trace(void* buf);
+int sifnn_conv3x3_fwd_fs(const float* in, const float* in_scale, const float* in_shift, const float* w,
+                         float* out, double* stats, void* wprep,
+                         int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+int sifnn_conv3x3_dgrad_fs(const float* dy, const float* w, float* dx, int accumulate, void* wprep,
+                           int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+
 /* Weight gradient.  `in`/in_scale/in_shift as in sifnn_conv3x3_fwd.  dw (Cout,Cin,3,3)
  * is overwritten; dbias (Cout) or NULL.  workspace: sifnn_conv3x3_wgrad_workspace()
  * bytes of scratch (per-CTA partial sums, reduced in a fixed order -> deterministic). */

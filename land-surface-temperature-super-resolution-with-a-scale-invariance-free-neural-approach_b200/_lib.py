@@ -14,7 +14,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsifnn_b200.so")
-SOURCES = ["core.cu", "conv3x3.cu", "conv3x3_tc.cu", "conv3x3_ff.cu", "wgrad.cu", "wgrad_tc.cu", "elementwise.cu", "loss.cu", "quality.cu", "adam.cu", "modelb.cu"]
+SOURCES = ["core.cu", "conv3x3.cu", "conv3x3_tc.cu", "conv3x3_ff.cu", "conv3x3_fs.cu", "wgrad.cu", "wgrad_tc.cu", "elementwise.cu", "loss.cu", "quality.cu", "adam.cu", "modelb.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared"]
 
@@ -77,6 +77,11 @@ SIGNATURES = {
     "sifnn_conv3x3_ff_trace": (None, [c_void_p]),
     "sifnn_conv3x3_fwd_ff": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
     "sifnn_conv3x3_dgrad_ff": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] + [c_int] * 5 + [c_void_p]),
+    "sifnn_conv3x3_fs_supported": (c_int, [c_int] * 4),
+    "sifnn_conv3x3_fs_config": (None, [c_int, c_int]),
+    "sifnn_conv3x3_fs_trace": (None, [c_void_p]),
+    "sifnn_conv3x3_fwd_fs": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
+    "sifnn_conv3x3_dgrad_fs": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] + [c_int] * 5 + [c_void_p]),
     "sifnn_conv3x3_dgrad_border": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
     "sifnn_conv3x3_wgrad_workspace": (c_size_t, [c_int] * 5),
     "sifnn_conv3x3_wgrad": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),

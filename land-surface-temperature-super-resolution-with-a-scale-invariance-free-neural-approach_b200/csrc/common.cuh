@@ -11,6 +11,8 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 int num_sms();
 unsigned long long launches();
+bool tc_split_tf32(int dgrad);              // operand precision of the round-2 tensor-core convolutions (core.cu)
+void tc_split_set(int fwd_tf32, int dgrad_tf32);
 
 // Tensor-core convolution with the weight split done beforehand (csrc/conv3x3_tc.cu).  The split weights depend only on the layer, so the
 // network plan prepares ALL layers of a pass in one launch (tc_prep_many) instead of one tiny launch in front of every convolution.
@@ -29,6 +31,16 @@ int ff_prep(const float* const* w, void* const* wprep, const int* K, const int* 
 int conv3x3_fwd_ff_prepped(const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, float* out, double* stats,
                            int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
 int conv3x3_dgrad_ff_prepped(const float* dy, const void* wprep, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
+
+// Fold + shift tensor-core convolution for widths that are multiples of 128 (csrc/conv3x3_fs.cu): ky in the MMA's N dimension, kx through shifted
+// operand views, rolling row sums in the epilogue; complete data gradient (padding adjoint included).
+bool conv3x3_fs_supported(int K, int O, int H, int W);
+size_t conv3x3_fs_wedge_bytes(int K, int O);
+int fs_prep(const float* const* w, void* const* wprep, float* const* wedge, const int* K, const int* O, const int* w_so, const int* w_sk, const int* flip, int n,
+            cudaStream_t st);
+int conv3x3_fwd_fs_prepped(const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, float* out, double* stats,
+                           int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
+int conv3x3_dgrad_fs_prepped(const float* dy, const void* wprep, const float* wedge, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
 
 inline cudaStream_t as_stream(sifnn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -508,12 +508,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs 
 
 // Operand precision of the 3-term split: BF16 (K = 16 per MMA; per-layer error ~5e-6) by default, TF32 (K = 8: twice the MMAs, ~4e-7) with
 // SIFNN_FF_TF32=1 or sifnn_conv3x3_ff_config(1, ...).  SIFNN_FF=0 turns the full-fold kernel off in the network plan (round-1 kernels; A/B runs).
-int g_ff_tf32 = -1, g_ff_max_ctas = 0, g_ff_ablate = 0;
+int g_ff_max_ctas = 0, g_ff_ablate = 0;
 unsigned long long* g_ff_trace = nullptr;
-bool ff_tf32() {
-    if (g_ff_tf32 < 0) { const char* e = getenv("SIFNN_FF_TF32"); g_ff_tf32 = (e && e[0] == '1') ? 1 : 0; }
-    return g_ff_tf32 == 1;
-}
 bool ff_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SIFNN_FF"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -549,7 +545,7 @@ bool ff_shape_ok(int K, int O, int H, int W) {
 int run_ff(int pad, const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, float* out, double* stats,
            int accumulate, int B, int K, int O, int H, int W, cudaStream_t st) {
     SIFNN_REQUIRE(ff_shape_ok(K, O, H, W), "conv3x3_ff: unsupported shape K=%d O=%d H=%d W=%d", K, O, H, W);
-    const bool bf = !ff_tf32();
+    const bool bf = !sifnn::tc_split_tf32(pad);
     const int KC = bf ? 16 : 8;
     SIFNN_REQUIRE(!in2 || (K1 % KC == 0 && K1 > 0 && K1 < K), "conv3x3_ff: the split point of a two-source input must be a multiple of %d", KC);
     FfArgs a{};
@@ -629,7 +625,7 @@ int ff_prep(const float* const* w, void* const* wprep, const int* K, const int* 
     for (int i0 = 0; i0 < n; i0 += FF_PREP_MAX) {
         FfPrepBatch b{};
         const int m = n - i0 < FF_PREP_MAX ? n - i0 : FF_PREP_MAX;
-        for (int i = 0; i < m; ++i) b.j[i] = FfPrepJob{w[i0 + i], wprep[i0 + i], K[i0 + i], O[i0 + i], w_so[i0 + i], w_sk[i0 + i], flip[i0 + i], ff_tf32() ? 0 : 1};
+        for (int i = 0; i < m; ++i) b.j[i] = FfPrepJob{w[i0 + i], wprep[i0 + i], K[i0 + i], O[i0 + i], w_so[i0 + i], w_sk[i0 + i], flip[i0 + i], tc_split_tf32(flip[i0 + i]) ? 0 : 1};
         ff_prep_kernel<<<dim3(32, m), 256, 0, st>>>(b);
         SIFNN_TRY(check_launch("ff_prep_kernel"));
     }
@@ -646,7 +642,7 @@ int conv3x3_dgrad_ff_prepped(const float* dy, const void* wprep, float* dx, int 
 
 }  // namespace sifnn
 
-extern "C" void sifnn_conv3x3_ff_config(int tf32, int max_ctas) { g_ff_tf32 = tf32 ? 1 : 0; g_ff_max_ctas = max_ctas; }
+extern "C" void sifnn_conv3x3_ff_config(int tf32, int max_ctas) { sifnn::tc_split_set(tf32, tf32); g_ff_max_ctas = max_ctas; }
 extern "C" void sifnn_conv3x3_ff_debug(int ablate) { g_ff_ablate = ablate; }
 extern "C" void sifnn_conv3x3_ff_trace(void* buf) { g_ff_trace = static_cast<unsigned long long*>(buf); }
 extern "C" int sifnn_conv3x3_ff_supported(int Cin, int Cout, int H, int W) { return sifnn::conv3x3_ff_supported(Cin, Cout, H, W) ? 1 : 0; }

@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 namespace sifnn {
 
@@ -27,6 +28,24 @@ int check_launch(const char* what) {
 }
 
 unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+// Operand precision of the 3-term split in the round-2 tensor-core convolutions, per direction (0 forward, 1 data gradient):
+// 1 = TF32 (K = 8 per MMA, per-layer error ~4e-7), 0 = BF16 (K = 16 per MMA: half the MMAs, ~5e-6).  -1 = not set yet: read the environment
+// (SIFNN_FF_TF32=1 both directions, SIFNN_FWD_TF32 / SIFNN_DGRAD_TF32 = 0 | 1 one direction).  Defaults: see tc_split_default().
+static int g_split_tf32[2] = {-1, -1};
+static int tc_split_default(int dgrad) { return dgrad ? 0 : 1; }
+bool tc_split_tf32(int dgrad) {
+    int& v = g_split_tf32[dgrad ? 1 : 0];
+    if (v < 0) {
+        v = tc_split_default(dgrad);
+        const char* e = getenv("SIFNN_FF_TF32");
+        if (e && (e[0] == '0' || e[0] == '1')) v = e[0] - '0';
+        e = getenv(dgrad ? "SIFNN_DGRAD_TF32" : "SIFNN_FWD_TF32");
+        if (e && (e[0] == '0' || e[0] == '1')) v = e[0] - '0';
+    }
+    return v == 1;
+}
+void tc_split_set(int fwd_tf32, int dgrad_tf32) { g_split_tf32[0] = fwd_tf32 ? 1 : 0; g_split_tf32[1] = dgrad_tf32 ? 1 : 0; }
 
 int num_sms() {
     static int n = 0;

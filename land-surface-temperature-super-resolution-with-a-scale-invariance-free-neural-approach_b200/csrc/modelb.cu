@@ -71,6 +71,17 @@ bool tc_enabled() {
     return g_tc_mode == 1;
 }
 
+// Which convolution kernel serves a layer (K = channels of the tensor that is read, O = channels written):
+//   FS  fold + shift (conv3x3_fs.cu): widths that are multiples of 128;  FF  full fold (conv3x3_ff.cu): 32- and 64-pixel-wide levels;
+//   TC  round-1 tcgen05 kernels (any other eligible shape, more than 64 input channels);  SIMT  fp32 direct convolution.
+enum ConvKind { KIND_SIMT = 0, KIND_TC = 1, KIND_FF = 2, KIND_FS = 3 };
+ConvKind conv_kind(int K, int O, int H, int W, bool tc_ok) {
+    if (!tc_enabled()) return KIND_SIMT;
+    if (sifnn::conv3x3_fs_supported(K, O, H, W)) return KIND_FS;
+    if (sifnn::conv3x3_ff_supported(K, O, H, W)) return KIND_FF;
+    return tc_ok ? KIND_TC : KIND_SIMT;
+}
+
 struct Carver {
     char* base;
     size_t off;
@@ -98,6 +109,7 @@ struct Workspace {
     void* wgrad_ws;
     void* wprep_f[SIFNN_MODELB_NCONV];  // hi/lo-split weights per layer, forward layout (tensor-core path; all prepared by ONE launch per pass)
     void* wprep_d[SIFNN_MODELB_NCONV];  // same, data-gradient layout (training only)
+    float* wedge_d[SIFNN_MODELB_NCONV]; // fp32 edge taps of the fold + shift data gradient (training only)
     size_t bytes;
 };
 
@@ -122,8 +134,10 @@ Workspace carve(const Net& n, void* base, int B, int H, int W, int train) {
     for (int i = 0; i < SIFNN_MODELB_NCONV; ++i)
         w.wprep_f[i] = c.take<char>(sifnn_conv3x3_tc_wprep_bytes((n.conv[i].cin + 7) / 8 * 8, n.conv[i].cout));
     if (train) {
-        for (int i = 0; i < SIFNN_MODELB_NCONV; ++i)
+        for (int i = 0; i < SIFNN_MODELB_NCONV; ++i) {
             w.wprep_d[i] = c.take<char>(sifnn_conv3x3_tc_wprep_bytes((n.conv[i].cout + 7) / 8 * 8, n.conv[i].cin));
+            w.wedge_d[i] = c.take<float>(sifnn::conv3x3_fs_wedge_bytes(n.conv[i].cout, n.conv[i].cin) / sizeof(float));
+        }
         for (int i = 0; i < SIFNN_MODELB_NBN; ++i) w.g[i] = c.take<float>((size_t)B * n.conv[i].cout * hw[n.conv[i].level]);
         for (int k = 0; k < 3; ++k) w.gR[k] = c.take<float>((size_t)B * n.d[k] * hw[k + 1]);
         for (int k = 0; k < 3; ++k) w.gU[k] = c.take<float>((size_t)B * n.d[3 - k] * hw[2 - k]);
@@ -211,17 +225,30 @@ extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* pa
         SIFNN_TRY(sifnn::check_launch("bn_eval_affine_all_kernel"));
     }
 
-    // tensor-core layers: split the weights of all of them in one launch
-    auto fwd_tc = [&](int i) {
+    // tensor-core layers: split the weights of all of them up front, one launch per kernel family
+    auto fwd_kind = [&](int i) {
         const ConvDesc& c = n.conv[i];
-        return tc_enabled() && c.cout <= 64 && sifnn_conv3x3_tc_supported(c.cin, c.cout, hs[c.level], ws[c.level]) != 0;
+        const bool tc_ok = c.cout <= 64 && sifnn_conv3x3_tc_supported(c.cin, c.cout, hs[c.level], ws[c.level]) != 0;
+        return conv_kind(c.cin, c.cout, hs[c.level], ws[c.level], tc_ok);
     };
     {
         sifnn::TcPrepJob jobs[SIFNN_MODELB_NCONV];
-        int nj = 0;
-        for (int i = 0; i < SIFNN_MODELB_NCONV; ++i)
-            if (fwd_tc(i)) jobs[nj++] = sifnn::tc_prep_job_fwd(params + n.w_off[i], w.wprep_f[i], n.conv[i].cin, n.conv[i].cout, ws[n.conv[i].level]);
+        const float* pw[2][SIFNN_MODELB_NCONV];
+        void* pp[2][SIFNN_MODELB_NCONV];
+        int pK[2][SIFNN_MODELB_NCONV], pO[2][SIFNN_MODELB_NCONV], pso[2][SIFNN_MODELB_NCONV], psk[2][SIFNN_MODELB_NCONV], pfl[2][SIFNN_MODELB_NCONV];
+        int nj = 0, np[2] = {0, 0};
+        for (int i = 0; i < SIFNN_MODELB_NCONV; ++i) {
+            const ConvKind k = fwd_kind(i);
+            if (k == KIND_TC) jobs[nj++] = sifnn::tc_prep_job_fwd(params + n.w_off[i], w.wprep_f[i], n.conv[i].cin, n.conv[i].cout, ws[n.conv[i].level]);
+            if (k == KIND_FF || k == KIND_FS) {
+                const int f = (k == KIND_FS) ? 1 : 0, j = np[f]++;
+                pw[f][j] = params + n.w_off[i]; pp[f][j] = w.wprep_f[i]; pK[f][j] = n.conv[i].cin; pO[f][j] = n.conv[i].cout;
+                pso[f][j] = n.conv[i].cin * 9; psk[f][j] = 9; pfl[f][j] = 0;
+            }
+        }
         SIFNN_TRY(sifnn::tc_prep_many(jobs, nj, st));
+        if (np[0]) SIFNN_TRY(sifnn::ff_prep(pw[0], pp[0], pK[0], pO[0], pso[0], psk[0], pfl[0], np[0], st));
+        if (np[1]) SIFNN_TRY(sifnn::fs_prep(pw[1], pp[1], nullptr, pK[1], pO[1], pso[1], psk[1], pfl[1], np[1], st));
     }
     // conv i reading `in` (plain if aff < 0, else BatchNorm+ReLU of layer `aff` applied on load)
     auto conv = [&](int i, const float* in, int aff, float* out) -> int {
@@ -231,12 +258,20 @@ extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* pa
         const float* isc = aff >= 0 ? w.scale + n.bn_off[aff] : nullptr;
         const float* ish = aff >= 0 ? w.shift + n.bn_off[aff] : nullptr;
         double* st_ptr = (bn && train) ? w.stats + 2 * n.bn_off[i] : nullptr;
-        if (fwd_tc(i)) {
-            SIFNN_TRY(sifnn::conv3x3_fwd_tc_prepped(in, isc, ish, w.wprep_f[i], bn ? nullptr : params + n.bias_off, out, st_ptr, B, c.cin, c.cout, hs[l],
-                                                    ws[l], st));
-        } else {
-            SIFNN_TRY(sifnn_conv3x3_fwd(in, isc, ish, params + n.w_off[i], bn ? nullptr : params + n.bias_off, out, st_ptr, B, c.cin, c.cout, hs[l],
-                                        ws[l], stream));
+        switch (fwd_kind(i)) {
+            case KIND_FS:
+                SIFNN_TRY(sifnn::conv3x3_fwd_fs_prepped(in, nullptr, 0, isc, ish, w.wprep_f[i], out, st_ptr, 0, B, c.cin, c.cout, hs[l], ws[l], st));
+                break;
+            case KIND_FF:
+                SIFNN_TRY(sifnn::conv3x3_fwd_ff_prepped(in, nullptr, 0, isc, ish, w.wprep_f[i], out, st_ptr, 0, B, c.cin, c.cout, hs[l], ws[l], st));
+                break;
+            case KIND_TC:
+                SIFNN_TRY(sifnn::conv3x3_fwd_tc_prepped(in, isc, ish, w.wprep_f[i], bn ? nullptr : params + n.bias_off, out, st_ptr, B, c.cin, c.cout, hs[l],
+                                                        ws[l], st));
+                break;
+            default:
+                SIFNN_TRY(sifnn_conv3x3_fwd(in, isc, ish, params + n.w_off[i], bn ? nullptr : params + n.bias_off, out, st_ptr, B, c.cin, c.cout, hs[l],
+                                            ws[l], stream));
         }
         if (bn && train) {
             const int64_t o = n.bn_off[i];
@@ -293,26 +328,48 @@ extern "C" int sifnn_modelb_backward(const sifnn_modelb_cfg* cfg, const float* p
         return sifnn_conv3x3_wgrad(in, aff >= 0 ? sc(aff) : nullptr, aff >= 0 ? sh(aff) : nullptr, g, grads + n.w_off[i],
                                    i == 17 ? grads + n.bias_off : nullptr, w.wgrad_ws, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
     };
-    auto dgrad_tc = [&](int i) {
+    auto dgrad_kind = [&](int i) {
         const ConvDesc& c = n.conv[i];
-        return i > 0 && tc_enabled() && sifnn_conv3x3_tc_supported(c.cout, c.cin, hs[c.level], ws[c.level]) != 0;
+        if (i == 0) return KIND_SIMT;
+        const bool tc_ok = sifnn_conv3x3_tc_supported(c.cout, c.cin, hs[c.level], ws[c.level]) != 0;
+        return conv_kind(c.cout, c.cin, hs[c.level], ws[c.level], tc_ok);
     };
-    {   // data-gradient weight splits of the layers this call touches, one launch (decoder = conv 11..17, encoder = conv 1..10)
+    {   // data-gradient weight splits of the layers this call touches, one launch per kernel family (decoder = conv 11..17, encoder = conv 1..10)
         sifnn::TcPrepJob jobs[SIFNN_MODELB_NCONV];
-        int nj = 0;
+        const float* pw[2][SIFNN_MODELB_NCONV];
+        void* pp[2][SIFNN_MODELB_NCONV];
+        float* pe[SIFNN_MODELB_NCONV];
+        int pK[2][SIFNN_MODELB_NCONV], pO[2][SIFNN_MODELB_NCONV], pso[2][SIFNN_MODELB_NCONV], psk[2][SIFNN_MODELB_NCONV], pfl[2][SIFNN_MODELB_NCONV];
+        int nj = 0, np[2] = {0, 0};
         const int lo = (phase == 2) ? 1 : ((phase == 1) ? 11 : 1), hi = (phase == 2) ? 10 : 17;
-        for (int i = lo; i <= hi; ++i)
-            if (dgrad_tc(i)) jobs[nj++] = sifnn::tc_prep_job_dgrad(params + n.w_off[i], w.wprep_d[i], n.conv[i].cin, n.conv[i].cout, ws[n.conv[i].level]);
+        for (int i = lo; i <= hi; ++i) {
+            const ConvKind k = dgrad_kind(i);
+            if (k == KIND_TC) jobs[nj++] = sifnn::tc_prep_job_dgrad(params + n.w_off[i], w.wprep_d[i], n.conv[i].cin, n.conv[i].cout, ws[n.conv[i].level]);
+            if (k == KIND_FF || k == KIND_FS) {
+                const int f = (k == KIND_FS) ? 1 : 0, j = np[f]++;
+                pw[f][j] = params + n.w_off[i]; pp[f][j] = w.wprep_d[i]; pK[f][j] = n.conv[i].cout; pO[f][j] = n.conv[i].cin;
+                pso[f][j] = 9; psk[f][j] = n.conv[i].cin * 9; pfl[f][j] = 1;
+                if (f == 1) pe[j] = w.wedge_d[i];
+            }
+        }
         SIFNN_TRY(sifnn::tc_prep_many(jobs, nj, st));
+        if (np[0]) SIFNN_TRY(sifnn::ff_prep(pw[0], pp[0], pK[0], pO[0], pso[0], psk[0], pfl[0], np[0], st));
+        if (np[1]) SIFNN_TRY(sifnn::fs_prep(pw[1], pp[1], pe, pK[1], pO[1], pso[1], psk[1], pfl[1], np[1], st));
     }
     auto dgrad = [&](int i, const float* g, float* dx, int accumulate) -> int {
         const ConvDesc& c = n.conv[i];
-        if (dgrad_tc(i)) {
-            // the tensor-core kernel folds the top/bottom row terms of the padding adjoint in as extra tap MMAs; the column terms (+ corners) follow
-            SIFNN_TRY(sifnn::conv3x3_dgrad_tc_main_prepped(g, w.wprep_d[i], dx, accumulate, B, c.cin, c.cout, hs[c.level], ws[c.level], st));
-            return sifnn::conv3x3_dgrad_border_cols(g, params + n.w_off[i], dx, B, c.cin, c.cout, hs[c.level], ws[c.level], st);
+        switch (dgrad_kind(i)) {
+            case KIND_FS:   // complete data gradient, padding adjoint included
+                return sifnn::conv3x3_dgrad_fs_prepped(g, w.wprep_d[i], w.wedge_d[i], dx, accumulate, B, c.cin, c.cout, hs[c.level], ws[c.level], st);
+            case KIND_FF:
+                return sifnn::conv3x3_dgrad_ff_prepped(g, w.wprep_d[i], dx, accumulate, B, c.cin, c.cout, hs[c.level], ws[c.level], st);
+            case KIND_TC:
+                // the round-1 kernel folds the top/bottom row terms of the padding adjoint in as extra tap MMAs; the column terms (+ corners) follow
+                SIFNN_TRY(sifnn::conv3x3_dgrad_tc_main_prepped(g, w.wprep_d[i], dx, accumulate, B, c.cin, c.cout, hs[c.level], ws[c.level], st));
+                return sifnn::conv3x3_dgrad_border_cols(g, params + n.w_off[i], dx, B, c.cin, c.cout, hs[c.level], ws[c.level], st);
+            default:
+                return sifnn_conv3x3_dgrad(g, params + n.w_off[i], dx, accumulate, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
         }
-        return sifnn_conv3x3_dgrad(g, params + n.w_off[i], dx, accumulate, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
     };
     // BatchNorm+ReLU backward of layer i: dY (gradient w.r.t. the activated output) -> dx (w.r.t. raw[i])
     auto bnbwd = [&](int i, const float* dY, float* dx) -> int {

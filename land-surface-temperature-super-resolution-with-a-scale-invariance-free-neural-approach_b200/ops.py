@@ -107,6 +107,32 @@ def conv3x3_dgrad_ff(dy, w, dx: Optional[torch.Tensor] = None, accumulate: bool 
     return dx
 
 
+def conv3x3_fwd_fs(x, w, in_scale=None, in_shift=None, stats: Optional[torch.Tensor] = None):
+    """Fold + shift tcgen05 forward (csrc/conv3x3_fs.cu), widths that are multiples of 128."""
+    _chk(x, w, in_scale, in_shift, stats)
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    lib = _lib.load()
+    wprep = torch.empty(lib.sifnn_conv3x3_tc_wprep_bytes(Cin, Cout), dtype=torch.uint8, device=x.device)
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device)
+    _lib.call("sifnn_conv3x3_fwd_fs", _p(x), _p(in_scale), _p(in_shift), _p(w), _p(out), _p(stats), _p(wprep), B, Cin, Cout, H, W, _s())
+    return out
+
+
+def conv3x3_dgrad_fs(dy, w, dx: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """Fold + shift tcgen05 data gradient, padding adjoint included (one launch)."""
+    _chk(dy, w, dx)
+    B, Cout, H, W = dy.shape
+    Cin = w.shape[1]
+    lib = _lib.load()
+    wprep = torch.empty(lib.sifnn_conv3x3_tc_wprep_bytes(Cout, Cin) + 2 * Cout * 3 * Cin * 4, dtype=torch.uint8, device=dy.device)
+    if dx is None:
+        dx = torch.empty((B, Cin, H, W), dtype=torch.float32, device=dy.device)
+        accumulate = False
+    _lib.call("sifnn_conv3x3_dgrad_fs", _p(dy), _p(w), _p(dx), 1 if accumulate else 0, _p(wprep), B, Cin, Cout, H, W, _s())
+    return dx
+
+
 def conv3x3_wgrad(x, dy, in_scale=None, in_shift=None, want_bias: bool = False):
     _chk(x, dy, in_scale, in_shift)
     B, Cin, H, W = x.shape

@@ -1,0 +1,107 @@
+"""Fold + shift tcgen05 convolution (csrc/conv3x3_fs.cu; widths that are multiples of 128): forward with replicate padding
+(model.py:135, nn.Conv2d(padding_mode='replicate')) and its complete autograd data gradient against torch fp64 on the CPU (-m gpu).
+
+Tolerances: max|a - b| / max|b|.  TF32 split: ~2e-6 measured -> 1e-5.  BF16 split: ~5e-6 measured -> 3e-5.  Both far inside the 1e-4 bar."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import sifnn_b200
+from sifnn_b200 import ops, _lib
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = {0: 3e-5, 1: 1e-5}   # keyed by tf32 flag
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def ref_conv(x, w):
+    return F.conv2d(F.pad(x.double(), (1, 1, 1, 1), mode="replicate"), w.double())
+
+
+@pytest.fixture(params=[0, 1], ids=["bf16x3", "tf32x3"])
+def prec(request):
+    lib = _lib.load()
+    lib.sifnn_conv3x3_fs_config(request.param, 0)
+    yield request.param
+    lib.sifnn_conv3x3_fs_config(0, 0)
+
+
+# (B, Cin, Cout, H, W): one / two / three pieces per row, 1 and 2 output groups per CTA, blockIdx.y > 1, ragged row partitions, single-row images
+SHAPES = [(2, 16, 16, 8, 128), (1, 32, 16, 6, 256), (2, 64, 32, 5, 128), (3, 16, 32, 16, 128), (1, 16, 16, 1, 128), (1, 16, 16, 2, 256),
+          (7, 16, 16, 5, 256), (1, 64, 64, 11, 128), (1, 32, 128, 4, 128), (3, 16, 16, 256, 256), (1, 32, 32, 33, 256), (2, 16, 16, 3, 384)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_fs_fwd_plain(shape, prec):
+    B, Cin, Cout, H, W = shape
+    x, w = rnd(B, Cin, H, W, seed=1), rnd(Cout, Cin, 3, 3, seed=2, scale=0.2)
+    y = ops.conv3x3_fwd_fs(x.cuda(), w.cuda())
+    assert rel_err(y, ref_conv(x, w)) < TOL[prec]
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 8, 128), (1, 32, 16, 6, 256), (2, 64, 32, 9, 128), (2, 16, 32, 40, 128), (1, 64, 64, 6, 256)])
+def test_fs_fwd_affine_stats(shape, prec):
+    B, Cin, Cout, H, W = shape
+    x, w = rnd(B, Cin, H, W, seed=4), rnd(Cout, Cin, 3, 3, seed=5, scale=0.2)
+    sc, sh = 1 + 0.3 * rnd(Cin, seed=6), 0.2 * rnd(Cin, seed=7)
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    y = ops.conv3x3_fwd_fs(x.cuda(), w.cuda(), sc.cuda(), sh.cuda(), stats)
+    a = F.relu(x.double() * sc.double()[None, :, None, None] + sh.double()[None, :, None, None])
+    ref = ref_conv(a, w)
+    assert rel_err(y, ref) < TOL[prec]
+    assert rel_err(stats[:Cout], ref.sum((0, 2, 3))) < 1e-4
+    assert rel_err(stats[Cout:], (ref * ref).sum((0, 2, 3))) < 3e-5
+
+
+DG_SHAPES = [(2, 16, 16, 8, 128), (1, 16, 32, 6, 256), (2, 64, 32, 5, 128), (1, 32, 64, 4, 128), (2, 32, 16, 7, 256), (1, 16, 16, 1, 128),
+             (2, 32, 16, 150, 256), (1, 128, 64, 5, 128), (2, 16, 16, 3, 384), (3, 64, 64, 4, 128)]
+
+
+@pytest.mark.parametrize("shape", DG_SHAPES)
+def test_fs_dgrad_complete(shape, prec):
+    """dy -> dx including the adjoint of the replicate padding (rows, columns, corners), plain and accumulating."""
+    B, Cin, Cout, H, W = shape
+    w, dy = rnd(Cout, Cin, 3, 3, seed=8, scale=0.2), rnd(B, Cout, H, W, seed=9)
+    x = torch.zeros(B, Cin, H, W, dtype=torch.float64, requires_grad=True)
+    (ref_conv(x, w) * dy.double()).sum().backward()
+    dx = ops.conv3x3_dgrad_fs(dy.cuda(), w.cuda())
+    assert rel_err(dx, x.grad) < TOL[prec]
+    base = rnd(B, Cin, H, W, seed=10)
+    acc = ops.conv3x3_dgrad_fs(dy.cuda(), w.cuda(), base.cuda().clone(), accumulate=True)
+    assert rel_err(acc, x.grad + base.double()) < TOL[prec]
+
+
+@pytest.mark.parametrize("max_ctas", [1, 2, 3, 7])
+def test_fs_long_strips_and_image_crossings(max_ctas):
+    """Few CTAs -> each walks many rows and crosses image boundaries."""
+    lib = _lib.load()
+    try:
+        for tf32 in (0, 1):
+            lib.sifnn_conv3x3_fs_config(tf32, max_ctas)
+            for (B, Cin, Cout, H, W) in [(3, 16, 16, 100, 256), (3, 32, 32, 37, 128)]:
+                x, w = rnd(B, Cin, H, W, seed=21), rnd(Cout, Cin, 3, 3, seed=22, scale=0.2)
+                sc, sh = 1 + 0.3 * rnd(Cin, seed=23), 0.2 * rnd(Cin, seed=24)
+                stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+                y = ops.conv3x3_fwd_fs(x.cuda(), w.cuda(), sc.cuda(), sh.cuda(), stats)
+                a = F.relu(x.double() * sc.double()[None, :, None, None] + sh.double()[None, :, None, None])
+                ref = ref_conv(a, w)
+                assert rel_err(y, ref) < TOL[tf32], (tf32, B, Cin, Cout, H, W)
+                assert rel_err(stats[:Cout], ref.sum((0, 2, 3))) < 1e-4
+                dy = rnd(B, Cout, H, W, seed=25)
+                xx = torch.zeros(B, Cin, H, W, dtype=torch.float64, requires_grad=True)
+                (ref_conv(xx, w) * dy.double()).sum().backward()
+                dx = ops.conv3x3_dgrad_fs(dy.cuda(), w.cuda())
+                assert rel_err(dx, xx.grad) < TOL[tf32], (tf32, B, Cin, Cout, H, W)
+    finally:
+        lib.sifnn_conv3x3_fs_config(0, 0)
+
+
+def test_fs_rejects_unsupported():
+    x, w = rnd(1, 16, 8, 64).cuda(), rnd(16, 16, 3, 3).cuda()
+    with pytest.raises(sifnn_b200.SifnnError):
+        ops.conv3x3_fwd_fs(x, w)

@@ -38,10 +38,12 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--old", action="store_true", help="also time the round-1 kernels")
+    ap.add_argument("--ff", action="store_true", help="also time the full-fold kernel on the wide layers")
     a = ap.parse_args()
     B = a.batch
     lib = sifnn_b200.load()
     lib.sifnn_conv3x3_ff_config(1 if a.tf32 else 0, 0)
+    lib.sifnn_conv3x3_fs_config(1 if a.tf32 else 0, 0)
     roof = (732.4e12 if a.tf32 else 1670.5e12) / 3
     print(f"# full-fold convolution, {'TF32' if a.tf32 else 'BF16'} 3-term split, B = {B}; roofline = max(FLOP / {roof / 1e12:.0f} TFLOP/s, bytes / 6457 GB/s)")
     tot = {}
@@ -56,7 +58,13 @@ def main():
         fl = 2.0 * B * ci * co * 9 * hw * hw
         byts = 4.0 * B * (ci + co) * hw * hw
         floor = max(fl / roof, byts / HBM)
-        fns = {"fwd_ff": lambda: ops.conv3x3_fwd_ff(x, w, sc, sh, stats), "dgrad_ff": lambda: ops.conv3x3_dgrad_ff(dy, w)}
+        if hw % 128 == 0:
+            fns = {"fwd_fs": lambda: ops.conv3x3_fwd_fs(x, w, sc, sh, stats), "dgrad_fs": lambda: ops.conv3x3_dgrad_fs(dy, w)}
+            if a.ff:
+                fns["fwd_ff"] = lambda: ops.conv3x3_fwd_ff(x, w, sc, sh, stats)
+                fns["dgrad_ff"] = lambda: ops.conv3x3_dgrad_ff(dy, w)
+        else:
+            fns = {"fwd_ff": lambda: ops.conv3x3_fwd_ff(x, w, sc, sh, stats), "dgrad_ff": lambda: ops.conv3x3_dgrad_ff(dy, w)}
         if a.old:
             fns["fwd_tc"] = lambda: ops.conv3x3_fwd_tc(x, w, None, sc, sh, stats)
             fns["dgrad_tc"] = lambda: ops.conv3x3_dgrad_tc(dy, w)
