@@ -80,8 +80,10 @@ int sifnn_conv3x3_dgrad_border(const float* dy, const float* w, float* dx,
  * Cin (forward) / Cout (data gradient) a multiple of 16 up to 64, the other channel count a multiple of 16 up to 128.
  * wprep: sifnn_conv3x3_tc_wprep_bytes() bytes of scratch. */
 int sifnn_conv3x3_ff_supported(int Cin, int Cout, int H, int W);
-/* tf32 != 0: TF32 split instead of BF16; max_ctas > 0 caps gridDim.x (tests: long row strips on small inputs), 0 = one CTA per SM */
-void sifnn_conv3x3_ff_config(int tf32, int max_ctas);
+/* kind: operand format of the 3-term split, 0 BF16, 1 TF32, 2 FP16 (forward only; the data gradient then uses BF16) -- sets BOTH round-2 kernels;
+ * max_ctas > 0 caps gridDim.x (tests: long row strips on small inputs), 0 = one CTA per SM.  Defaults: forward FP16, data gradient BF16
+ * (environment: SIFNN_FWD_SPLIT / SIFNN_DGRAD_SPLIT = bf16 | tf32 | fp16). */
+void sifnn_conv3x3_ff_config(int kind, int max_ctas);
 /* debug: ablation bits for pipeline studies (1 no MMAs, 2 no epilogue math, 4 no TMEM loads, 8 no transform, 16 no stores, 32 L2-resident loads); results are then wrong */
 void sifnn_conv3x3_ff_debug(int ablate);
 /* debug: device buffer of 11 * 256 uint64 that receives clock64 stamps of CTA (0,0) per pipeline step (tools/trace_ff.py), or NULL */
@@ -97,7 +99,7 @@ int sifnn_conv3x3_dgrad_ff(const float* dy, const float* w, float* dx, int accum
  * Same semantics as sifnn_conv3x3_fwd (no bias) and the COMPLETE sifnn_conv3x3_dgrad.  Channel limits as for the full-fold kernel.
  * wprep: sifnn_conv3x3_tc_wprep_bytes() bytes; the data gradient needs 2 * Cout * 3 * Cin * 4 bytes more (fp32 edge taps). */
 int sifnn_conv3x3_fs_supported(int Cin, int Cout, int H, int W);
-void sifnn_conv3x3_fs_config(int tf32, int max_ctas);
+void sifnn_conv3x3_fs_config(int kind, int max_ctas);
 /* debug: device buffer of 16 * 256 uint64 for clock64 stamps of CTA (0,0) per pipeline step (tools/trace_fs.py), or NULL */
 void sifnn_conv3x3_fs_trace(void* buf);
 int sifnn_conv3x3_fwd_fs(const float* in, const float* in_scale, const float* in_shift, const float* w,

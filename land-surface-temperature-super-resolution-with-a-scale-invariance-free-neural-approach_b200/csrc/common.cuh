@@ -11,8 +11,8 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 int num_sms();
 unsigned long long launches();
-bool tc_split_tf32(int dgrad);              // operand precision of the round-2 tensor-core convolutions (core.cu)
-void tc_split_set(int fwd_tf32, int dgrad_tf32);
+int tc_split_kind(int dgrad);               // operand format of the round-2 tensor-core convolutions: 0 BF16, 1 TF32, 2 FP16 (core.cu)
+void tc_split_set(int fwd_kind, int dgrad_kind);
 
 // Tensor-core convolution with the weight split done beforehand (csrc/conv3x3_tc.cu).  The split weights depend only on the layer, so the
 // network plan prepares ALL layers of a pass in one launch (tc_prep_many) instead of one tiny launch in front of every convolution.

@@ -27,6 +27,7 @@
 #include "tc_common.cuh"
 
 #include <cstdlib>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -121,16 +122,24 @@ struct FfIter {
     }
 };
 
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t h, float& lo_elem, float& hi_elem) {
+    asm("{\n\t.reg .f16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(lo_elem), "=f"(hi_elem) : "r"(h));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
     return r;
 }
 
-template <bool BF, int NG, int PAD, bool AFFINE, bool STATS, bool T2, bool DBG>
+template <int KIND, int NG, int PAD, bool AFFINE, bool STATS, bool T2, bool DBG>
 __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs a, const __grid_constant__ CUtensorMap tmap,
                                                                    const __grid_constant__ CUtensorMap tmap2) {
-    constexpr int KC = BF ? 16 : 8;
+    constexpr int KC = (KIND == 1) ? 8 : 16;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int nchunks = a.K / KC;
     const FfLayout L = ff_layout(nchunks, NG, KC, T2);
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs 
         }
     } else if (warp == FF_MMA_WARP) {
         // ======================= MMA issuer (one thread): 3 MMAs of N = 144 per (chunk, output group) =======================
-        constexpr uint32_t idesc = BF ? make_idesc_bf16(128, FF_N) : make_idesc(128, FF_N);
+        constexpr uint32_t idesc = KIND == 0 ? make_idesc_bf16(128, FF_N) : (KIND == 1 ? make_idesc(128, FF_N) : make_idesc_f16(128, FF_N));
         mbar_wait(w_full, 0);
         int seq = 0;
         for (int step = 0; step < nsteps; ++step) {
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs 
                         const uint64_t da_hi = make_desc(a_hi, 128 * 16, 128), da_lo = make_desc(a_hi + FF_A_TILE, 128 * 16, 128);
                         const uint64_t dw_hi = make_desc(w_hi, FF_N * 16, 128), dw_lo = make_desc(w_hi + FF_W_TILE, FF_N * 16, 128);
                         if (DBG && (a.ablate & 1)) {
-                        } else if (BF) {
+                        } else if (KIND != 1) {
                             umma_bf16(d, da_lo, dw_hi, idesc, c > 0 ? 1u : 0u);   // small terms first
                             umma_bf16(d, da_hi, dw_lo, idesc, 1u);
                             umma_bf16(d, da_hi, dw_hi, idesc, 1u);
@@ -271,7 +280,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs 
                 if (!(DBG && (a.ablate & 8)))
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    if constexpr (BF) {
+                    if constexpr (KIND != 1) {
                         uint32_t hp[4], lp[4];
 #pragma unroll
                         for (int e = 0; e < 8; e += 2) {
@@ -280,10 +289,18 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs 
                                 t0 = sifnn::act_affine_relu(t0, sc_s[c0 + 8 * q + e], sh_s[c0 + 8 * q + e]);
                                 t1 = sifnn::act_affine_relu(t1, sc_s[c0 + 8 * q + e + 1], sh_s[c0 + 8 * q + e + 1]);
                             }
-                            const uint32_t h = pack_bf16x2(t0, t1);
-                            const float r0 = t0 - __uint_as_float(h << 16), r1 = t1 - __uint_as_float(h & 0xffff0000u);
-                            hp[e >> 1] = h;
-                            lp[e >> 1] = pack_bf16x2(r0, r1);
+                            if constexpr (KIND == 0) {
+                                const uint32_t h = pack_bf16x2(t0, t1);
+                                const float r0 = t0 - __uint_as_float(h << 16), r1 = t1 - __uint_as_float(h & 0xffff0000u);
+                                hp[e >> 1] = h;
+                                lp[e >> 1] = pack_bf16x2(r0, r1);
+                            } else {   // FP16: 11 + 11 significant bits; the three products share one accumulator here, so the residual is NOT scaled
+                                const uint32_t h = pack_f16x2(t0, t1);
+                                float f0, f1;
+                                unpack_f16x2(h, f0, f1);
+                                hp[e >> 1] = h;
+                                lp[e >> 1] = pack_f16x2(t0 - f0, t1 - f1);
+                            }
                         }
                         *reinterpret_cast<uint4*>(a_hi + (size_t)(q * 128 + p) * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                         *reinterpret_cast<uint4*>(a_hi + FF_A_TILE + (size_t)(q * 128 + p) * 16) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
@@ -434,10 +451,15 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs 
                         *reinterpret_cast<float4*>(carry_out + (size_t)(row - ya) * (16 * NG) + chan) = make_float4(v[0], v[1], v[2], v[3]);
                     } else {
                         float* op = a.out + ((size_t)b * a.O + obase) * plane + (size_t)row * W + x;
+                        float old[CS];
+                        if (accum) {   // all loads first: one memory round trip instead of CS dependent ones
+#pragma unroll
+                            for (int j = 0; j < CS; ++j) old[j] = __ldcg(op + (size_t)j * plane);
+                        }
 #pragma unroll
                         for (int j = 0; j < CS; ++j, op += plane) {
                             float o = v[j];
-                            if (accum) o += *op;
+                            if (accum) o += old[j];
                             if (!(DBG && (a.ablate & 16))) *op = o;
                             if constexpr (STATS) { s1[g][j] += o; s2[g][j] = fmaf(o, o, s2[g][j]); }
                         }
@@ -516,14 +538,14 @@ bool ff_enabled() {
     return v == 1;
 }
 
-template <bool BF, int NG, int PAD, bool AFFINE, bool STATS, bool T2>
+template <int KIND, int NG, int PAD, bool AFFINE, bool STATS, bool T2>
 int launch_ff(const FfArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, int gx, int gy, cudaStream_t st) {
-    constexpr int KC = BF ? 16 : 8;
+    constexpr int KC = (KIND == 1) ? 8 : 16;
     const FfLayout L = ff_layout(a.K / KC, NG, KC, T2);
-    auto kern = conv3x3_ff_kernel<BF, NG, PAD, AFFINE, STATS, T2, false>;
+    auto kern = conv3x3_ff_kernel<KIND, NG, PAD, AFFINE, STATS, T2, false>;
     if (a.ablate || a.trace) {
         // the traced / ablatable build exists for the plain bf16 / tf32 forward only (tools/trace_ff.py, tools/ablate_ff.py)
-        if constexpr (PAD == 0 && !AFFINE && !STATS) kern = conv3x3_ff_kernel<BF, NG, PAD, AFFINE, STATS, T2, true>;
+        if constexpr (PAD == 0 && !AFFINE && !STATS) kern = conv3x3_ff_kernel<KIND, NG, PAD, AFFINE, STATS, T2, true>;
     }
     SIFNN_REQUIRE(L.total <= 227 * 1024, "conv3x3_ff: shared-memory budget exceeded (K=%d)", a.K);
     SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
@@ -531,10 +553,16 @@ int launch_ff(const FfArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, i
     return sifnn::check_launch("conv3x3_ff_kernel");
 }
 
-template <bool BF, int PAD, bool AFFINE, bool STATS>
+template <int KIND, int PAD, bool AFFINE, bool STATS>
 int dispatch_ff2(const FfArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, int NG, int gx, int gy, bool t2, cudaStream_t st) {
-    if (NG == 1) return t2 ? launch_ff<BF, 1, PAD, AFFINE, STATS, true>(a, tm1, tm2, gx, gy, st) : launch_ff<BF, 1, PAD, AFFINE, STATS, false>(a, tm1, tm2, gx, gy, st);
-    return t2 ? launch_ff<BF, 2, PAD, AFFINE, STATS, true>(a, tm1, tm2, gx, gy, st) : launch_ff<BF, 2, PAD, AFFINE, STATS, false>(a, tm1, tm2, gx, gy, st);
+    if (NG == 1) return t2 ? launch_ff<KIND, 1, PAD, AFFINE, STATS, true>(a, tm1, tm2, gx, gy, st) : launch_ff<KIND, 1, PAD, AFFINE, STATS, false>(a, tm1, tm2, gx, gy, st);
+    return t2 ? launch_ff<KIND, 2, PAD, AFFINE, STATS, true>(a, tm1, tm2, gx, gy, st) : launch_ff<KIND, 2, PAD, AFFINE, STATS, false>(a, tm1, tm2, gx, gy, st);
+}
+template <int KIND>
+int dispatch_ff1(int pad, bool affine, bool stats, const FfArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, int NG, int gx, int gy, bool t2, cudaStream_t st) {
+    if (pad == 1) return dispatch_ff2<KIND, 1, false, false>(a, tm1, tm2, NG, gx, gy, t2, st);
+    if (affine) return stats ? dispatch_ff2<KIND, 0, true, true>(a, tm1, tm2, NG, gx, gy, t2, st) : dispatch_ff2<KIND, 0, true, false>(a, tm1, tm2, NG, gx, gy, t2, st);
+    return stats ? dispatch_ff2<KIND, 0, false, true>(a, tm1, tm2, NG, gx, gy, t2, st) : dispatch_ff2<KIND, 0, false, false>(a, tm1, tm2, NG, gx, gy, t2, st);
 }
 
 bool ff_shape_ok(int K, int O, int H, int W) {
@@ -545,8 +573,9 @@ bool ff_shape_ok(int K, int O, int H, int W) {
 int run_ff(int pad, const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, float* out, double* stats,
            int accumulate, int B, int K, int O, int H, int W, cudaStream_t st) {
     SIFNN_REQUIRE(ff_shape_ok(K, O, H, W), "conv3x3_ff: unsupported shape K=%d O=%d H=%d W=%d", K, O, H, W);
-    const bool bf = !sifnn::tc_split_tf32(pad);
-    const int KC = bf ? 16 : 8;
+    const int kind = sifnn::tc_split_kind(pad);
+    SIFNN_REQUIRE(!(pad == 1 && kind == 2), "conv3x3_ff: the FP16 split is for the forward form only (gradients can be tiny)");
+    const int KC = (kind == 1) ? 8 : 16;
     SIFNN_REQUIRE(!in2 || (K1 % KC == 0 && K1 > 0 && K1 < K), "conv3x3_ff: the split point of a two-source input must be a multiple of %d", KC);
     FfArgs a{};
     a.in_scale = in_scale; a.in_shift = in_shift; a.wprep = static_cast<const unsigned char*>(wprep); a.out = out; a.stats = stats;
@@ -558,7 +587,7 @@ int run_ff(int pad, const float* in, const float* in2, int K1, const float* in_s
     a.trace = g_ff_trace;
     // output groups per CTA: two where the weights fit; TF32 with 64 input channels keeps one (8 chunks of weights + operand ring)
     int NG = (O >= 32) ? 2 : 1;
-    if (!bf && K > 32) NG = 1;
+    if (kind == 1 && K > 32) NG = 1;
     const int gy = O / (16 * NG);
     int gx = sifnn::num_sms() / gy;
     if (g_ff_max_ctas > 0 && gx > g_ff_max_ctas) gx = g_ff_max_ctas;   // tests: long strips on small inputs
@@ -572,25 +601,19 @@ int run_ff(int pad, const float* in, const float* in2, int K1, const float* in_s
     else tm2 = tm1;
     const bool t2 = (W == 256);
     const bool affine = in_scale != nullptr;
-    if (pad == 0) {
-        if (bf) {
-            if (affine) return stats ? dispatch_ff2<true, 0, true, true>(a, tm1, tm2, NG, gx, gy, t2, st) : dispatch_ff2<true, 0, true, false>(a, tm1, tm2, NG, gx, gy, t2, st);
-            return stats ? dispatch_ff2<true, 0, false, true>(a, tm1, tm2, NG, gx, gy, t2, st) : dispatch_ff2<true, 0, false, false>(a, tm1, tm2, NG, gx, gy, t2, st);
-        }
-        if (affine) return stats ? dispatch_ff2<false, 0, true, true>(a, tm1, tm2, NG, gx, gy, t2, st) : dispatch_ff2<false, 0, true, false>(a, tm1, tm2, NG, gx, gy, t2, st);
-        return stats ? dispatch_ff2<false, 0, false, true>(a, tm1, tm2, NG, gx, gy, t2, st) : dispatch_ff2<false, 0, false, false>(a, tm1, tm2, NG, gx, gy, t2, st);
-    }
-    return bf ? dispatch_ff2<true, 1, false, false>(a, tm1, tm2, NG, gx, gy, t2, st) : dispatch_ff2<false, 1, false, false>(a, tm1, tm2, NG, gx, gy, t2, st);
+    if (kind == 0) return dispatch_ff1<0>(pad, affine, stats != nullptr, a, tm1, tm2, NG, gx, gy, t2, st);
+    if (kind == 1) return dispatch_ff1<1>(pad, affine, stats != nullptr, a, tm1, tm2, NG, gx, gy, t2, st);
+    return dispatch_ff1<2>(pad, affine, stats != nullptr, a, tm1, tm2, NG, gx, gy, t2, st);
 }
 
 // split weights in the exact shared-memory image of the kernel: [O / 16][chunk][hi, lo][2 q][144 = (tap, o % 16)][8 bf16 | 4 tf32]
-struct FfPrepJob { const float* w; void* wprep; int K, O, w_so, w_sk, flip, bf; };
+struct FfPrepJob { const float* w; void* wprep; int K, O, w_so, w_sk, flip, kind; };
 constexpr int FF_PREP_MAX = 24;
 struct FfPrepBatch { FfPrepJob j[FF_PREP_MAX]; };
 
 __global__ void __launch_bounds__(256) ff_prep_kernel(const __grid_constant__ FfPrepBatch batch) {
     const FfPrepJob& J = batch.j[blockIdx.y];
-    const int KC = J.bf ? 16 : 8, E = KC / 2;
+    const int KC = (J.kind == 1) ? 8 : 16, E = KC / 2;
     const int nchunks = J.K / KC;
     const int total = (J.O / 16) * nchunks * 2 * 2 * FF_N * E;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -603,10 +626,14 @@ __global__ void __launch_bounds__(256) ff_prep_kernel(const __grid_constant__ Ff
         const int grp = i / nchunks;
         const int tap = n / 16, o = grp * 16 + (n % 16), k = c * KC + q * E + e;
         const float v = __ldg(J.w + (size_t)o * J.w_so + (size_t)k * J.w_sk + (J.flip ? 8 - tap : tap));
-        if (J.bf) {
+        if (J.kind == 0) {
             unsigned short h, l;
             bf16_split(v, h, l);
             static_cast<unsigned short*>(J.wprep)[idx] = lo ? l : h;
+        } else if (J.kind == 2) {
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn(v - __half2float(h));
+            static_cast<__half*>(J.wprep)[idx] = lo ? l : h;
         } else {
             const float hi = tf32_hi(v);
             static_cast<float*>(J.wprep)[idx] = lo ? v - hi : hi;
@@ -625,7 +652,7 @@ int ff_prep(const float* const* w, void* const* wprep, const int* K, const int* 
     for (int i0 = 0; i0 < n; i0 += FF_PREP_MAX) {
         FfPrepBatch b{};
         const int m = n - i0 < FF_PREP_MAX ? n - i0 : FF_PREP_MAX;
-        for (int i = 0; i < m; ++i) b.j[i] = FfPrepJob{w[i0 + i], wprep[i0 + i], K[i0 + i], O[i0 + i], w_so[i0 + i], w_sk[i0 + i], flip[i0 + i], tc_split_tf32(flip[i0 + i]) ? 0 : 1};
+        for (int i = 0; i < m; ++i) b.j[i] = FfPrepJob{w[i0 + i], wprep[i0 + i], K[i0 + i], O[i0 + i], w_so[i0 + i], w_sk[i0 + i], flip[i0 + i], tc_split_kind(flip[i0 + i])};
         ff_prep_kernel<<<dim3(32, m), 256, 0, st>>>(b);
         SIFNN_TRY(check_launch("ff_prep_kernel"));
     }
@@ -642,7 +669,7 @@ int conv3x3_dgrad_ff_prepped(const float* dy, const void* wprep, float* dx, int 
 
 }  // namespace sifnn
 
-extern "C" void sifnn_conv3x3_ff_config(int tf32, int max_ctas) { sifnn::tc_split_set(tf32, tf32); g_ff_max_ctas = max_ctas; }
+extern "C" void sifnn_conv3x3_ff_config(int kind, int max_ctas) { sifnn::tc_split_set(kind, kind == 2 ? 0 : kind); g_ff_max_ctas = max_ctas; }
 extern "C" void sifnn_conv3x3_ff_debug(int ablate) { g_ff_ablate = ablate; }
 extern "C" void sifnn_conv3x3_ff_trace(void* buf) { g_ff_trace = static_cast<unsigned long long*>(buf); }
 extern "C" int sifnn_conv3x3_ff_supported(int Cin, int Cout, int H, int W) { return sifnn::conv3x3_ff_supported(Cin, Cout, H, W) ? 1 : 0; }

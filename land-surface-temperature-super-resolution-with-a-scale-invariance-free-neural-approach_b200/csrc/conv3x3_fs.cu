@@ -25,6 +25,7 @@
 #include "tc_common.cuh"
 
 #include <cstdlib>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -125,12 +126,23 @@ __device__ __forceinline__ uint32_t fs_pack_bf16x2(float lo_elem, float hi_elem)
     return r;
 }
 
+// FP16 pair: pack (round to nearest) and unpack
+__device__ __forceinline__ uint32_t fs_pack_f16x2(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+__device__ __forceinline__ void fs_unpack_f16x2(uint32_t h, float& lo_elem, float& hi_elem) {
+    asm("{\n\t.reg .f16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(lo_elem), "=f"(hi_elem) : "r"(h));
+}
+constexpr float FS_LO_SCALE = 2048.f;   // FP16 split: the residual (and the weights' residual) is stored times 2^11, the cross block is rescaled by the epilogue
+
 // one pixel of one chunk: raw fp32 (channel stride FS_PX) -> BatchNorm affine + ReLU -> hi / lo split -> the two 16-byte units of the pixel
-template <bool BF, bool AFFINE>
+template <int KIND, bool AFFINE>
 __device__ __forceinline__ void fs_convert_pixel(const float* raw, unsigned char* a_hi, int jdst, const float* sc, const float* sh) {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        if constexpr (BF) {
+        if constexpr (KIND != 1) {
             uint32_t hp[4], lp[4];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
@@ -139,10 +151,18 @@ __device__ __forceinline__ void fs_convert_pixel(const float* raw, unsigned char
                     t0 = sifnn::act_affine_relu(t0, sc[8 * q + e], sh[8 * q + e]);
                     t1 = sifnn::act_affine_relu(t1, sc[8 * q + e + 1], sh[8 * q + e + 1]);
                 }
-                const uint32_t h = fs_pack_bf16x2(t0, t1);
-                const float r0 = t0 - __uint_as_float(h << 16), r1 = t1 - __uint_as_float(h & 0xffff0000u);
-                hp[e >> 1] = h;
-                lp[e >> 1] = fs_pack_bf16x2(r0, r1);
+                if constexpr (KIND == 0) {
+                    const uint32_t h = fs_pack_bf16x2(t0, t1);
+                    const float r0 = t0 - __uint_as_float(h << 16), r1 = t1 - __uint_as_float(h & 0xffff0000u);
+                    hp[e >> 1] = h;
+                    lp[e >> 1] = fs_pack_bf16x2(r0, r1);
+                } else {
+                    const uint32_t h = fs_pack_f16x2(t0, t1);
+                    float f0, f1;
+                    fs_unpack_f16x2(h, f0, f1);
+                    hp[e >> 1] = h;
+                    lp[e >> 1] = fs_pack_f16x2((t0 - f0) * FS_LO_SCALE, (t1 - f1) * FS_LO_SCALE);
+                }
             }
             *reinterpret_cast<uint4*>(a_hi + (size_t)(q * FS_PX + jdst) * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
             *reinterpret_cast<uint4*>(a_hi + FS_A_TILE + (size_t)(q * FS_PX + jdst) * 16) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
@@ -161,10 +181,10 @@ __device__ __forceinline__ void fs_convert_pixel(const float* raw, unsigned char
     }
 }
 
-template <bool BF, int NG, int PAD, bool AFFINE, bool STATS, bool DBG>
+template <int KIND, int NG, int PAD, bool AFFINE, bool STATS, bool DBG>
 __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const FsArgs a, const __grid_constant__ CUtensorMap tmap,
                                                                    const __grid_constant__ CUtensorMap tmap2) {
-    constexpr int KC = BF ? 16 : 8;
+    constexpr int KC = (KIND == 1) ? 8 : 16;
     constexpr int NPROD = FS_XF_WARPS + 1 + (PAD == 1 ? FS_EDGE_WARPS : 0);   // warps that read a raw stage and arrive on the operand barrier
     constexpr int NSLOT = (NG == 1) ? 5 : 2;     // TMEM ring: 96 NG columns per row piece
     constexpr int SLOT = 96 * NG, HALF = 48 * NG;
@@ -243,8 +263,8 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
         // The tensor pipe executes one of these MMAs per ~111 clocks and its queue is shallow, so every clock this thread spends between two
         // steps is a clock the pipe idles: one thread does everything (no warp-wide polls, no __syncwarp), its waits spin, and the descriptors
         // are advanced by constants instead of being rebuilt.
-        constexpr uint32_t idesc1 = BF ? make_idesc_bf16(128, SLOT) : make_idesc(128, SLOT);
-        constexpr uint32_t idesc2 = BF ? make_idesc_bf16(128, HALF) : make_idesc(128, HALF);
+        constexpr uint32_t idesc1 = KIND == 0 ? make_idesc_bf16(128, SLOT) : (KIND == 1 ? make_idesc(128, SLOT) : make_idesc_f16(128, SLOT));
+        constexpr uint32_t idesc2 = KIND == 0 ? make_idesc_bf16(128, HALF) : (KIND == 1 ? make_idesc(128, HALF) : make_idesc_f16(128, HALF));
         if (lane == 0) {
             mbar_wait_spin(w_full, 0);
             // start-address field = low 14 bits in 16-byte units; every offset below stays inside the 256 KB window, so plain 64-bit adds advance it
@@ -275,7 +295,7 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
                     const uint64_t dw = dw0 + (uint64_t)(c * 3 * (W_TILE / 16));
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
-                        if (BF) {
+                        if (KIND != 1) {
                             umma_bf16(d, da_hi + kx, dw + kx * (W_TILE / 16), idesc1, (c > 0 || kx > 0) ? 1u : 0u);   // hi x [hi ; lo]: also initialises the cross block
                             umma_bf16(d + HALF, da_lo + kx, dw + kx * (W_TILE / 16), idesc2, 1u);
                         } else {
@@ -303,7 +323,7 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
                 mbar_wait(raw_full + rs, rr.phase);
                 if (p == 0 && c == 0) FS_STAMP(2, step);
                 const float* raw = reinterpret_cast<const float*>(raw_s + (size_t)rs * L.raw_stage) + 4 + p;
-                fs_convert_pixel<BF, AFFINE>(raw, a_s + (size_t)as * 2 * FS_A_TILE, 4 + p, sc_s + c * KC, sh_s + c * KC);
+                fs_convert_pixel<KIND, AFFINE>(raw, a_s + (size_t)as * 2 * FS_A_TILE, 4 + p, sc_s + c * KC, sh_s + c * KC);
                 fence_proxy_async();           // this thread's st.shared -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(raw_empty + rs); mbar_arrive(a_full + as); }
@@ -325,7 +345,7 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
                     const int jdst = lane == 0 ? 3 : 132;
                     int jsrc = jdst;
                     if (PAD == 0) { if (lane == 0 && img_l) jsrc = 4; if (lane == 1 && img_r) jsrc = 131; }
-                    fs_convert_pixel<BF, AFFINE>(raw + jsrc, a_s + (size_t)as * 2 * FS_A_TILE, jdst, sc_s + c * KC, sh_s + c * KC);
+                    fs_convert_pixel<KIND, AFFINE>(raw + jsrc, a_s + (size_t)as * 2 * FS_A_TILE, jdst, sc_s + c * KC, sh_s + c * KC);
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -420,7 +440,7 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) Gk[ky][j] = hi[ky][j] + cr[ky][j];
+                        for (int j = 0; j < 8; ++j) Gk[ky][j] = (KIND == 2) ? fmaf(cr[ky][j], 1.f / FS_LO_SCALE, hi[ky][j]) : hi[ky][j] + cr[ky][j];
                 }
                 if (g == NG - 1) {
                     tc_fence_before();
@@ -452,10 +472,15 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
                 }
                 auto emit = [&](int row, const float* v) {
                     float* op = orow + (size_t)(g * 16) * plane + (size_t)row * W;
+                    float old[8];
+                    if (accum) {   // all eight loads first: one memory round trip instead of eight dependent ones
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) old[j] = __ldcg(op + (size_t)j * plane);
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j, op += plane) {
                         float o = v[j];
-                        if (accum) o += *op;
+                        if (accum) o += old[j];
                         *op = o;
                         if constexpr (STATS) { s1[g][j] += o; s2[g][j] = fmaf(o, o, s2[g][j]); }
                     }
@@ -501,13 +526,13 @@ bool fs_enabled() {
     return v == 1;
 }
 
-template <bool BF, int NG, int PAD, bool AFFINE, bool STATS>
+template <int KIND, int NG, int PAD, bool AFFINE, bool STATS>
 int launch_fs(const FsArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, int gx, int gy, cudaStream_t st) {
-    constexpr int KC = BF ? 16 : 8;
+    constexpr int KC = (KIND == 1) ? 8 : 16;
     const FsLayout L = fs_layout(a.K / KC, NG, KC, PAD == 1);
-    auto kern = conv3x3_fs_kernel<BF, NG, PAD, AFFINE, STATS, false>;
+    auto kern = conv3x3_fs_kernel<KIND, NG, PAD, AFFINE, STATS, false>;
     if (a.trace) {
-        if constexpr (PAD == 0 && !AFFINE && !STATS && NG == 1) kern = conv3x3_fs_kernel<BF, NG, PAD, AFFINE, STATS, true>;   // traced build: plain forward only
+        if constexpr (PAD == 0 && !AFFINE && !STATS && NG == 1) kern = conv3x3_fs_kernel<KIND, NG, PAD, AFFINE, STATS, true>;   // traced build: plain forward only
     }
     SIFNN_REQUIRE(L.total <= 227 * 1024, "conv3x3_fs: shared-memory budget exceeded (K=%d)", a.K);
     SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
@@ -515,27 +540,34 @@ int launch_fs(const FsArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, i
     return sifnn::check_launch("conv3x3_fs_kernel");
 }
 
-template <bool BF, int PAD, bool AFFINE, bool STATS>
+template <int KIND, int PAD, bool AFFINE, bool STATS>
 int dispatch_fs2(const FsArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, int NG, int gx, int gy, cudaStream_t st) {
-    if (NG == 1) return launch_fs<BF, 1, PAD, AFFINE, STATS>(a, tm1, tm2, gx, gy, st);
-    return launch_fs<BF, 2, PAD, AFFINE, STATS>(a, tm1, tm2, gx, gy, st);
+    if (NG == 1) return launch_fs<KIND, 1, PAD, AFFINE, STATS>(a, tm1, tm2, gx, gy, st);
+    return launch_fs<KIND, 2, PAD, AFFINE, STATS>(a, tm1, tm2, gx, gy, st);
+}
+template <int KIND>
+int dispatch_fs1(int pad, bool affine, bool stats, const FsArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, int NG, int gx, int gy, cudaStream_t st) {
+    if (pad == 1) return dispatch_fs2<KIND, 1, false, false>(a, tm1, tm2, NG, gx, gy, st);
+    if (affine) return stats ? dispatch_fs2<KIND, 0, true, true>(a, tm1, tm2, NG, gx, gy, st) : dispatch_fs2<KIND, 0, true, false>(a, tm1, tm2, NG, gx, gy, st);
+    return stats ? dispatch_fs2<KIND, 0, false, true>(a, tm1, tm2, NG, gx, gy, st) : dispatch_fs2<KIND, 0, false, false>(a, tm1, tm2, NG, gx, gy, st);
 }
 
 bool fs_shape_ok(int K, int O, int H, int W) {
     return (W % 128 == 0) && W >= 128 && W <= 4096 && (K % 16 == 0) && K >= 16 && K <= FS_MAX_K && (O % 16 == 0) && O >= 16 && O <= 128 && (O == 16 || O % 32 == 0) && H >= 1;
 }
 
-int fs_groups(int K, int O, bool bf) {   // output groups of 16 channels per CTA
+int fs_groups(int K, int O, int kind) {   // output groups of 16 channels per CTA
     if (O < 32) return 1;
-    if (!bf && K > 32) return 1;          // TF32: 8 chunks of weights + operand ring do not fit with two groups
+    if (kind == 1 && K > 32) return 1;          // TF32: 8 chunks of weights + operand ring do not fit with two groups
     return 2;
 }
 
 int run_fs(int pad, const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, const float* wedge, float* out,
            double* stats, int accumulate, int B, int K, int O, int H, int W, cudaStream_t st) {
     SIFNN_REQUIRE(fs_shape_ok(K, O, H, W), "conv3x3_fs: unsupported shape K=%d O=%d H=%d W=%d", K, O, H, W);
-    const bool bf = !sifnn::tc_split_tf32(pad);
-    const int KC = bf ? 16 : 8;
+    const int kind = sifnn::tc_split_kind(pad);
+    SIFNN_REQUIRE(!(pad == 1 && kind == 2), "conv3x3_fs: the FP16 split is for the forward form only (gradients can be tiny)");
+    const int KC = (kind == 1) ? 8 : 16;
     SIFNN_REQUIRE(!in2 || (K1 % KC == 0 && K1 > 0 && K1 < K), "conv3x3_fs: the split point of a two-source input must be a multiple of %d", KC);
     FsArgs a{};
     a.in_scale = in_scale; a.in_shift = in_shift; a.wprep = static_cast<const unsigned char*>(wprep); a.wedge = wedge; a.out = out; a.stats = stats;
@@ -543,7 +575,7 @@ int run_fs(int pad, const float* in, const float* in2, int K1, const float* in_s
     a.nrows = B * H;
     a.K1 = in2 ? K1 : K;
     a.trace = g_fs_trace;
-    const int NG = fs_groups(K, O, bf);
+    const int NG = fs_groups(K, O, kind);
     const int gy = O / (16 * NG);
     int gx = sifnn::num_sms() / gy;
     if (g_fs_max_ctas > 0 && gx > g_fs_max_ctas) gx = g_fs_max_ctas;   // tests: long strips on small inputs
@@ -554,28 +586,22 @@ int run_fs(int pad, const float* in, const float* in2, int K1, const float* in_s
     if (in2) SIFNN_REQUIRE(encode_planes_map(&tm2, in2, W, H, (long long)B * (K - K1), FS_PX, 1, KC), "conv3x3_fs: cuTensorMapEncodeTiled failed (second source)");
     else tm2 = tm1;
     const bool affine = in_scale != nullptr;
-    if (pad == 0) {
-        if (bf) {
-            if (affine) return stats ? dispatch_fs2<true, 0, true, true>(a, tm1, tm2, NG, gx, gy, st) : dispatch_fs2<true, 0, true, false>(a, tm1, tm2, NG, gx, gy, st);
-            return stats ? dispatch_fs2<true, 0, false, true>(a, tm1, tm2, NG, gx, gy, st) : dispatch_fs2<true, 0, false, false>(a, tm1, tm2, NG, gx, gy, st);
-        }
-        if (affine) return stats ? dispatch_fs2<false, 0, true, true>(a, tm1, tm2, NG, gx, gy, st) : dispatch_fs2<false, 0, true, false>(a, tm1, tm2, NG, gx, gy, st);
-        return stats ? dispatch_fs2<false, 0, false, true>(a, tm1, tm2, NG, gx, gy, st) : dispatch_fs2<false, 0, false, false>(a, tm1, tm2, NG, gx, gy, st);
-    }
-    SIFNN_REQUIRE(wedge, "conv3x3_fs: the data-gradient form needs the edge weights");
-    return bf ? dispatch_fs2<true, 1, false, false>(a, tm1, tm2, NG, gx, gy, st) : dispatch_fs2<false, 1, false, false>(a, tm1, tm2, NG, gx, gy, st);
+    SIFNN_REQUIRE(pad == 0 || wedge, "conv3x3_fs: the data-gradient form needs the edge weights");
+    if (kind == 0) return dispatch_fs1<0>(pad, affine, stats != nullptr, a, tm1, tm2, NG, gx, gy, st);
+    if (kind == 1) return dispatch_fs1<1>(pad, affine, stats != nullptr, a, tm1, tm2, NG, gx, gy, st);
+    return dispatch_fs1<2>(pad, affine, stats != nullptr, a, tm1, tm2, NG, gx, gy, st);
 }
 
 // Split weights in the exact shared-memory image of the kernel:
 //   wprep [gy][chunk][kx][2 q][row = (s, ky, g, o): s * 48 NG + (ky * NG + g) * 16 + o][8 bf16 | 4 tf32]
 //   wedge [gy][edge][k][(ky * NG + g) * 16 + o] fp32 (data gradient): tap (ky, kx = 2) for the left edge, (ky, kx = 0) for the right edge
-struct FsPrepJob { const float* w; void* wprep; float* wedge; int K, O, NG, w_so, w_sk, flip, bf; };
+struct FsPrepJob { const float* w; void* wprep; float* wedge; int K, O, NG, w_so, w_sk, flip, kind; };
 constexpr int FS_PREP_MAX = 24;
 struct FsPrepBatch { FsPrepJob j[FS_PREP_MAX]; };
 
 __global__ void __launch_bounds__(256) fs_prep_kernel(const __grid_constant__ FsPrepBatch batch) {
     const FsPrepJob& J = batch.j[blockIdx.y];
-    const int KC = J.bf ? 16 : 8, E = KC / 2, NG = J.NG;
+    const int KC = (J.kind == 1) ? 8 : 16, E = KC / 2, NG = J.NG;
     const int nchunks = J.K / KC, gy = J.O / (16 * NG), rows = 96 * NG;
     const int total = gy * nchunks * 3 * 2 * rows * E;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -591,10 +617,14 @@ __global__ void __launch_bounds__(256) fs_prep_kernel(const __grid_constant__ Fs
         const int ky = rr / (16 * NG), g = (rr / 16) % NG, o = (y * NG + g) * 16 + (rr % 16), k = c * KC + q * E + e;
         const int tap = ky * 3 + kx;
         const float v = __ldg(J.w + (size_t)o * J.w_so + (size_t)k * J.w_sk + (J.flip ? 8 - tap : tap));
-        if (J.bf) {
+        if (J.kind == 0) {
             unsigned short h, l;
             bf16_split(v, h, l);
             static_cast<unsigned short*>(J.wprep)[idx] = lo ? l : h;
+        } else if (J.kind == 2) {
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn((v - __half2float(h)) * FS_LO_SCALE);
+            static_cast<__half*>(J.wprep)[idx] = lo ? l : h;
         } else {
             const float hi = tf32_hi(v);
             static_cast<float*>(J.wprep)[idx] = lo ? v - hi : hi;
@@ -629,9 +659,9 @@ int fs_prep(const float* const* w, void* const* wprep, float* const* wedge, cons
         FsPrepBatch b{};
         const int m = n - i0 < FS_PREP_MAX ? n - i0 : FS_PREP_MAX;
         for (int i = 0; i < m; ++i) {
-            const bool bf = !tc_split_tf32(flip[i0 + i]);   // flip == 1: data-gradient layout
-            b.j[i] = FsPrepJob{w[i0 + i], wprep[i0 + i], wedge ? wedge[i0 + i] : nullptr, K[i0 + i], O[i0 + i], fs_groups(K[i0 + i], O[i0 + i], bf), w_so[i0 + i], w_sk[i0 + i],
-                               flip[i0 + i], bf ? 1 : 0};
+            const int kind = tc_split_kind(flip[i0 + i]);   // flip == 1: data-gradient layout
+            b.j[i] = FsPrepJob{w[i0 + i], wprep[i0 + i], wedge ? wedge[i0 + i] : nullptr, K[i0 + i], O[i0 + i], fs_groups(K[i0 + i], O[i0 + i], kind), w_so[i0 + i], w_sk[i0 + i],
+                               flip[i0 + i], kind};
         }
         fs_prep_kernel<<<dim3(32, m), 256, 0, st>>>(b);
         SIFNN_TRY(check_launch("fs_prep_kernel"));
@@ -649,7 +679,7 @@ int conv3x3_dgrad_fs_prepped(const float* dy, const void* wprep, const float* we
 
 }  // namespace sifnn
 
-extern "C" void sifnn_conv3x3_fs_config(int tf32, int max_ctas) { sifnn::tc_split_set(tf32, tf32); g_fs_max_ctas = max_ctas; }
+extern "C" void sifnn_conv3x3_fs_config(int kind, int max_ctas) { sifnn::tc_split_set(kind, kind == 2 ? 0 : kind); g_fs_max_ctas = max_ctas; }
 extern "C" void sifnn_conv3x3_fs_trace(void* buf) { g_fs_trace = static_cast<unsigned long long*>(buf); }
 extern "C" int sifnn_conv3x3_fs_supported(int Cin, int Cout, int H, int W) { return sifnn::conv3x3_fs_supported(Cin, Cout, H, W) ? 1 : 0; }
 

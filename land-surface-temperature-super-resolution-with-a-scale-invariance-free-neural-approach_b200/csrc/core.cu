@@ -29,23 +29,28 @@ int check_launch(const char* what) {
 
 unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
-// Operand precision of the 3-term split in the round-2 tensor-core convolutions, per direction (0 forward, 1 data gradient):
-// 1 = TF32 (K = 8 per MMA, per-layer error ~4e-7), 0 = BF16 (K = 16 per MMA: half the MMAs, ~5e-6).  -1 = not set yet: read the environment
-// (SIFNN_FF_TF32=1 both directions, SIFNN_FWD_TF32 / SIFNN_DGRAD_TF32 = 0 | 1 one direction).  Defaults: see tc_split_default().
-static int g_split_tf32[2] = {-1, -1};
-static int tc_split_default(int dgrad) { return dgrad ? 0 : 1; }
-bool tc_split_tf32(int dgrad) {
-    int& v = g_split_tf32[dgrad ? 1 : 0];
+// Operand format of the 3-term split in the round-2 tensor-core convolutions, per direction (0 forward, 1 data gradient):
+//   0 BF16 (K = 16 per MMA; 16 significant bits, fp32 range; per-layer error ~5e-6)
+//   1 TF32 (K =  8 per MMA: twice the MMAs; 22 bits; ~4e-7)
+//   2 FP16 (K = 16 per MMA; 22 bits like TF32 at the MMA count of BF16; the residual is scaled by 2^11 so it never goes subnormal; needs
+//           |value| < 65504: fine for z-scored inputs / BatchNorm outputs / weights, NOT for gradients, whose magnitudes can be tiny)
+// Defaults: forward FP16 -- the gradients of weights that feed a train-mode BatchNorm amplify forward rounding ~1000x, BF16 fails the per-tensor
+// gradient check of tests/test_gpu_model.py there; data gradient BF16.  Environment: SIFNN_FWD_SPLIT / SIFNN_DGRAD_SPLIT = bf16 | tf32 | fp16.
+static int g_split[2] = {-1, -1};
+int tc_split_kind(int dgrad) {
+    int& v = g_split[dgrad ? 1 : 0];
     if (v < 0) {
-        v = tc_split_default(dgrad);
-        const char* e = getenv("SIFNN_FF_TF32");
-        if (e && (e[0] == '0' || e[0] == '1')) v = e[0] - '0';
-        e = getenv(dgrad ? "SIFNN_DGRAD_TF32" : "SIFNN_FWD_TF32");
-        if (e && (e[0] == '0' || e[0] == '1')) v = e[0] - '0';
+        v = dgrad ? 0 : 2;
+        const char* e = getenv(dgrad ? "SIFNN_DGRAD_SPLIT" : "SIFNN_FWD_SPLIT");
+        if (e) {
+            if (e[0] == 'b' || e[0] == 'B') v = 0;
+            else if (e[0] == 't' || e[0] == 'T') v = 1;
+            else if (e[0] == 'f' || e[0] == 'F') v = 2;
+        }
     }
-    return v == 1;
+    return v;
 }
-void tc_split_set(int fwd_tf32, int dgrad_tf32) { g_split_tf32[0] = fwd_tf32 ? 1 : 0; g_split_tf32[1] = dgrad_tf32 ? 1 : 0; }
+void tc_split_set(int fwd_kind, int dgrad_kind) { g_split[0] = fwd_kind; g_split[1] = dgrad_kind; }
 
 int num_sms() {
     static int n = 0;

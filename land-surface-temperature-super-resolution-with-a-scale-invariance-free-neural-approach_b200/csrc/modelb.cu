@@ -214,7 +214,6 @@ extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* pa
     const Workspace w = carve(n, workspace, B, H, W, train);
     cudaStream_t st = sifnn::as_stream(stream);
     const int hs[4] = {H, H / 2, H / 4, H / 8}, ws[4] = {W, W / 2, W / 4, W / 8};
-
     if (train) {
         SIFNN_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(double) * 2 * n.bn_total, st));
     } else {

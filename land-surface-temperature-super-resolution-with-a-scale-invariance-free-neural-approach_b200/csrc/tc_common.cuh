@@ -155,6 +155,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// D = F32, A/B = FP16 (format 0), K-major both
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // x = hi + lo with hi, lo in BF16 (round to nearest): 16 significant bits; returns hi in the low, ... packed helpers below
 __device__ __forceinline__ void bf16_split(float x, unsigned short& hi, unsigned short& lo) {
     unsigned short h;

@@ -1,7 +1,8 @@
 """Full-fold tcgen05 convolution (csrc/conv3x3_ff.cu): forward with replicate padding (model.py:135, nn.Conv2d(padding_mode='replicate'))
 and its complete autograd data gradient, against torch fp64 on the CPU (-m gpu).
 
-Tolerances: max|a - b| / max|b|.  TF32 split: 2e-6 measured -> 1e-5.  BF16 split: ~5e-6 measured -> 3e-5.  Both far inside the 1e-4 bar."""
+Tolerances: max|a - b| / max|b|.  TF32 and FP16 splits (22 significant bits): ~2e-6 measured -> 1e-5.  BF16 split (16 bits): ~5e-6 measured -> 3e-5.
+All far inside the 1e-4 bar."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -11,7 +12,8 @@ from sifnn_b200 import ops, _lib
 from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
-TOL = {0: 3e-5, 1: 1e-5}   # keyed by tf32 flag
+TOL = {0: 3e-5, 1: 1e-5, 2: 1e-5}      # forward, keyed by the split kind: 0 BF16, 1 TF32, 2 FP16 (forward only)
+TOL_DG = {0: 3e-5, 1: 1e-5, 2: 3e-5}   # data gradient: kind 2 runs the BF16 split there
 
 
 def rnd(*shape, seed=0, scale=1.0):
@@ -23,12 +25,12 @@ def ref_conv(x, w):
     return F.conv2d(F.pad(x.double(), (1, 1, 1, 1), mode="replicate"), w.double())
 
 
-@pytest.fixture(params=[0, 1], ids=["bf16x3", "tf32x3"])
+@pytest.fixture(params=[0, 1, 2], ids=["bf16x3", "tf32x3", "fp16x3"])
 def prec(request):
     lib = _lib.load()
     lib.sifnn_conv3x3_ff_config(request.param, 0)
     yield request.param
-    lib.sifnn_conv3x3_ff_config(0, 0)
+    lib.sifnn_conv3x3_ff_config(2, 0)   # library default: FP16 forward, BF16 data gradient
 
 
 # (B, Cin, Cout, H, W): every width class (4 / 2 / 1 segments per tile, two tiles per row), 1 and 2 output groups per CTA, blockIdx.y > 1,
@@ -72,10 +74,10 @@ def test_ff_dgrad_complete(shape, prec):
     x = torch.zeros(B, Cin, H, W, dtype=torch.float64, requires_grad=True)
     (ref_conv(x, w) * dy.double()).sum().backward()
     dx = ops.conv3x3_dgrad_ff(dy.cuda(), w.cuda())
-    assert rel_err(dx, x.grad) < TOL[prec]
+    assert rel_err(dx, x.grad) < TOL_DG[prec]
     base = rnd(B, Cin, H, W, seed=10)
     acc = ops.conv3x3_dgrad_ff(dy.cuda(), w.cuda(), base.cuda().clone(), accumulate=True)
-    assert rel_err(acc, x.grad + base.double()) < TOL[prec]
+    assert rel_err(acc, x.grad + base.double()) < TOL_DG[prec]
 
 
 @pytest.mark.parametrize("max_ctas", [1, 2, 3, 7])
@@ -83,7 +85,7 @@ def test_ff_long_strips_and_image_crossings(max_ctas):
     """Few CTAs -> each walks many rows: strips longer than the 64-row carry window, ranges that cross image boundaries."""
     lib = _lib.load()
     try:
-        for tf32 in (0, 1):
+        for tf32 in (0, 1, 2):
             lib.sifnn_conv3x3_ff_config(tf32, max_ctas)
             for (B, Cin, Cout, H, W) in [(3, 16, 16, 100, 256), (5, 16, 32, 20, 64), (3, 32, 16, 37, 128), (9, 16, 16, 8, 32)]:
                 x, w = rnd(B, Cin, H, W, seed=21), rnd(Cout, Cin, 3, 3, seed=22, scale=0.2)
@@ -98,21 +100,21 @@ def test_ff_long_strips_and_image_crossings(max_ctas):
                 xx = torch.zeros(B, Cin, H, W, dtype=torch.float64, requires_grad=True)
                 (ref_conv(xx, w) * dy.double()).sum().backward()
                 dx = ops.conv3x3_dgrad_ff(dy.cuda(), w.cuda())
-                assert rel_err(dx, xx.grad) < TOL[tf32], (tf32, B, Cin, Cout, H, W)
+                assert rel_err(dx, xx.grad) < TOL_DG[tf32], (tf32, B, Cin, Cout, H, W)
     finally:
-        lib.sifnn_conv3x3_ff_config(0, 0)
+        lib.sifnn_conv3x3_ff_config(2, 0)   # library default: FP16 forward, BF16 data gradient
 
 
 def test_ff_matches_simt_kernel():
-    """Same inputs through the strict-fp32 SIMT kernel and the full-fold kernel (TF32 split)."""
+    """Same inputs through the strict-fp32 SIMT kernel and the full-fold kernel (FP16 split, the training default)."""
     lib = _lib.load()
-    lib.sifnn_conv3x3_ff_config(1, 0)
+    lib.sifnn_conv3x3_ff_config(2, 0)
     try:
         x, w = rnd(2, 32, 32, 256, seed=11).cuda(), rnd(16, 32, 3, 3, seed=12, scale=0.2).cuda()
         a, b = ops.conv3x3_fwd(x, w), ops.conv3x3_fwd_ff(x, w)
         assert rel_err(b, a) < 5e-6
     finally:
-        lib.sifnn_conv3x3_ff_config(0, 0)
+        lib.sifnn_conv3x3_ff_config(2, 0)   # library default: FP16 forward, BF16 data gradient
 
 
 def test_ff_rejects_unsupported():

@@ -35,6 +35,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--tf32", action="store_true")
+    ap.add_argument("--kind", type=int, default=-1, help="0 BF16, 1 TF32, 2 FP16 forward + BF16 data gradient (default)")
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--old", action="store_true", help="also time the round-1 kernels")
@@ -42,10 +43,11 @@ def main():
     a = ap.parse_args()
     B = a.batch
     lib = sifnn_b200.load()
-    lib.sifnn_conv3x3_ff_config(1 if a.tf32 else 0, 0)
-    lib.sifnn_conv3x3_fs_config(1 if a.tf32 else 0, 0)
-    roof = (732.4e12 if a.tf32 else 1670.5e12) / 3
-    print(f"# full-fold convolution, {'TF32' if a.tf32 else 'BF16'} 3-term split, B = {B}; roofline = max(FLOP / {roof / 1e12:.0f} TFLOP/s, bytes / 6457 GB/s)")
+    kind = a.kind if a.kind >= 0 else (1 if a.tf32 else 2)
+    lib.sifnn_conv3x3_ff_config(kind, 0)
+    lib.sifnn_conv3x3_fs_config(kind, 0)
+    roof = (732.4e12 if kind == 1 else 1670.5e12) / 3
+    print(f"# full-fold convolution, {['BF16', 'TF32', 'FP16 forward / BF16 data gradient'][kind]} 3-term split, B = {B}; roofline = max(FLOP / {roof / 1e12:.0f} TFLOP/s, bytes / 6457 GB/s)")
     tot = {}
     for ci, co, hw in LAYERS:
         if a.only and a.only != f"{ci}x{co}x{hw}":

@@ -7,6 +7,8 @@ import sifnn_b200
 from sifnn_b200 import _lib
 
 lib = sifnn_b200.load()
+kind = int(os.environ.get('KIND', '2'))
+lib.sifnn_conv3x3_fs_config(kind, 0)
 B = 32
 for sh in (sys.argv[1:] or ["16x16x256", "32x16x256", "64x32x128"]):
     ci, co, hw = (int(v) for v in sh.split("x"))
