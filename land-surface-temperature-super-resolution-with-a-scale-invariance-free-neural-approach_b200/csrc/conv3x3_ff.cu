@@ -62,7 +62,7 @@ struct FfArgs {
 
 // Shared-memory carve-up, identical on host and device
 struct FfLayout {
-    int xs, xbuf, carry_l, carry_out, w, a, raw, total;
+    int xs, xbuf, stat, carry_l, carry_out, w, a, raw, total;
     int AS, RS, raw_stage;
 };
 __host__ __device__ inline FfLayout ff_layout(int nchunks, int NG, int KC, bool T2) {
@@ -72,6 +72,7 @@ __host__ __device__ inline FfLayout ff_layout(int nchunks, int NG, int KC, bool 
     L.xs = off; off += 4 * NG * 2 * FF_CS * 4;                    // rolling state of the deferred tile-edge pixel (two-tile rows only)
     off = (off + 127) & ~127;
     L.xbuf = off; off += 4 * 2 * 4 * 2 * 3 * FF_CS * 4;       // quadrant-edge exchange [quarter][parity][quad][kind][3 ky][4]
+    L.stat = off; off += 4 * 2 * 16 * NG * 4;                    // per-quadrant partial BatchNorm sums of the CTA
     L.carry_l = off; if (T2) off += (FF_MAX_STRIP + 2) * 3 * 16 * NG * 4;
     L.carry_out = off; if (T2) off += FF_MAX_STRIP * 16 * NG * 4;
     off = (off + 1023) & ~1023;
@@ -507,17 +508,25 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs 
             it.next();
         }
         if constexpr (STATS) if (a.stats) {
+            // per-channel sums of this CTA: lanes by shuffle, the four quadrant warps through shared memory in a fixed order, one fp64 atomic per channel and CTA
+            float* part = reinterpret_cast<float*>(smem + L.stat);   // [quad][stat][NG * 16]
 #pragma unroll
             for (int g = 0; g < NG; ++g)
 #pragma unroll
                 for (int j = 0; j < CS; ++j) {
                     const float t1 = sifnn::warp_sum(s1[g][j]), t2 = sifnn::warp_sum(s2[g][j]);
                     if (lane == 0) {
-                        const int o = (blockIdx.y * NG + g) * 16 + cq * CS + j;
-                        atomicAdd(a.stats + o, (double)t1);
-                        atomicAdd(a.stats + a.O + o, (double)t2);
+                        part[(quad * 2 + 0) * 16 * NG + g * 16 + cq * CS + j] = t1;
+                        part[(quad * 2 + 1) * 16 * NG + g * 16 + cq * CS + j] = t2;
                     }
                 }
+            asm volatile("bar.sync 5, 512;" ::: "memory");   // the sixteen epilogue warps
+            if (tid < 2 * 16 * NG) {
+                const int stat = tid / (16 * NG), ch = tid - stat * 16 * NG;
+                const double v = (double)part[(0 * 2 + stat) * 16 * NG + ch] + (double)part[(1 * 2 + stat) * 16 * NG + ch] + (double)part[(2 * 2 + stat) * 16 * NG + ch] +
+                                 (double)part[(3 * 2 + stat) * 16 * NG + ch];
+                atomicAdd(a.stats + (size_t)stat * a.O + blockIdx.y * NG * 16 + ch, v);
+            }
         }
     }
     tc_fence_before();

@@ -56,7 +56,7 @@ struct FsArgs {
 };
 
 struct FsLayout {
-    int edge, w, a, raw, total;
+    int edge, stat, w, a, raw, total;
     int AS, RS, raw_stage;
 };
 __host__ __device__ inline FsLayout fs_layout(int nchunks, int NG, int KC, bool pad1) {
@@ -64,6 +64,7 @@ __host__ __device__ inline FsLayout fs_layout(int nchunks, int NG, int KC, bool 
     int off = 1024;               // [0, 1024): mbarriers + TMEM slot
     off += 2 * FS_MAX_K * 4;      // BatchNorm scale / shift of the input channels
     L.edge = off; if (pad1) off += FS_ES * 2 * 48 * NG * 4;
+    L.stat = off; if (!pad1) off += 4 * 2 * 16 * NG * 4;   // per-quadrant partial BatchNorm sums of the CTA
     off = (off + 1023) & ~1023;
     L.w = off; off += nchunks * 3 * 2 * 96 * NG * 16;
     L.AS = (NG == 1) ? (2 * nchunks < 8 ? (2 * nchunks < 4 ? 4 : 2 * nchunks) : 8) : 2 * nchunks;
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
             const bool emit_last = (r == H - 1) && (yb == H);
             const int slot = rc.idx;
             if (tid == 0) FS_STAMP(14, step);
-            mbar_wait_spin(acc_full + slot, rc.phase);
+            mbar_wait(acc_full + slot, rc.phase);   // suspending wait: the epilogue runs behind the MMAs with five slots of slack, a spin would only take issue slots from the transformers
             tc_fence_after();
             if (tid == 0) FS_STAMP(7, step);
             const uint32_t tcol = tlane + slot * SLOT;
@@ -497,17 +498,26 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
             it.next();
         }
         if constexpr (STATS) if (a.stats) {
+            // per-channel sums of this CTA: lanes by shuffle, the four quadrant warps through shared memory in a fixed order, then ONE fp64 atomic per
+            // channel and CTA (148 per address instead of 592: the serialised atomics were ~10 us of a 16-channel layer)
+            float* part = reinterpret_cast<float*>(smem + L.stat);   // [quad][stat][NG * 16]
 #pragma unroll
             for (int g = 0; g < NG; ++g)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float t1 = sifnn::warp_sum(s1[g][j]), t2 = sifnn::warp_sum(s2[g][j]);
                     if (lane == 0) {
-                        const int o = (blockIdx.y * NG + g) * 16 + half * 8 + j;
-                        atomicAdd(a.stats + o, (double)t1);
-                        atomicAdd(a.stats + a.O + o, (double)t2);
+                        part[(quad * 2 + 0) * 16 * NG + g * 16 + half * 8 + j] = t1;
+                        part[(quad * 2 + 1) * 16 * NG + g * 16 + half * 8 + j] = t2;
                     }
                 }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps
+            if (tid < 2 * 16 * NG) {
+                const int stat = tid / (16 * NG), ch = tid - stat * 16 * NG;
+                const double v = (double)part[(0 * 2 + stat) * 16 * NG + ch] + (double)part[(1 * 2 + stat) * 16 * NG + ch] + (double)part[(2 * 2 + stat) * 16 * NG + ch] +
+                                 (double)part[(3 * 2 + stat) * 16 * NG + ch];
+                atomicAdd(a.stats + (size_t)stat * a.O + blockIdx.y * NG * 16 + ch, v);
+            }
         }
     }
     tc_fence_before();
