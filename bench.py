@@ -29,6 +29,15 @@ import torch  # noqa: E402
 
 PATCH_MPIX = 256 * 256 / 1e6
 FWD_GFLOP, STEP_GFLOP = 3.605, 10.78  # per patch, SURVEY section 8d
+# ncu --set full summaries (profiles/) of one launch of each kernel class, used for roofline.traffic
+NCU_SUMMARIES = {"conv3x3_fs_kernel fwd": "r2l_ncu_full_conv3x3_fs_fwd_16x16x256_summary.csv",
+                 "conv3x3_fs_kernel dgrad": "r2l_ncu_full_conv3x3_fs_fwd_16x16x256_summary.csv",
+                 "conv3x3_ff_kernel fwd": "r2j_ncu_full_conv3x3_ff_16x16x256_summary.csv",
+                 "conv3x3_ff_kernel dgrad": "r2j_ncu_full_conv3x3_ff_16x16x256_summary.csv",
+                 "wgrad_tc_kernel": "r1l_ncu_full_wgrad_tc_32x16x256_summary.csv",
+                 "wgrad_kernel": "r1i_ncu_full_wgrad_16x16x256_summary.csv",
+                 "conv3x3_tc_kernel fwd": "r1j_ncu_full_conv3x3_tc_64x32x128_summary.csv",
+                 "conv3x3_tc_kernel dgrad": "r1q_ncu_full_conv3x3_tcx_dgrad_16x16x256_summary.csv"}
 HYPER = {"train_sr1": ("sr1", 0.99, -0.5, 1e-3), "train_sr2": ("sr2", 0.5, -0.25, 1e-4)}
 
 
@@ -100,46 +109,79 @@ def make_batches(n_batches, batch, seed):
 # --------------------------------------------------------------------------------------------------
 # reference arm: the CPU path the reference would run
 # --------------------------------------------------------------------------------------------------
+def reference_impl():
+    """The CPU implementation timed by the reference arm and the cpu_baseline leg: the reference's OWN model.py / utils.py (byte copies under
+    oracle/_ref/, made by oracle/make_ref.py wherever /root/reference exists) driven in the order of its train_step; the oracle port otherwise."""
+    try:
+        import ref_runner as R
+        if R.available():
+            R.load()
+            return "reference", R
+    except Exception as e:   # a missing third-party module of utils.py on this host: say so and fall back
+        sys.stderr.write(f"bench: reference modules unusable ({e!r}); timing the oracle port\n")
+    return "port", None
+
+
+def cpu_train_stepper(mode, batch):
+    import sifnn_oracle as O
+    kind, alpha, gamma, lr = HYPER[mode]
+    which, R = reference_impl()
+    sd = O.init_state_dict(0)
+    tr = R.RefTrainer(kind, alpha, gamma, lr, state_dict=sd) if R else O.Trainer(sd, kind, alpha, gamma, lr)
+    lst, up, ndvi = O.synthetic_batch(batch)
+    return which, (lambda: tr.step(lst, up, ndvi))
+
+
+def cpu_infer_stepper(batch):
+    import sifnn_oracle as O
+    which, R = reference_impl()
+    sd = O.init_state_dict(0)
+    x = torch.randn(batch, 2, 256, 256, generator=torch.Generator().manual_seed(1234))
+    if R:
+        m = R.build_model(sd).eval()
+
+        def step():
+            with torch.inference_mode():
+                m(x)
+    else:
+        def step():
+            with torch.inference_mode():
+                O.forward(sd, x, train=False)
+    return which, step
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import sifnn_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     mode = args.mode
-    if mode == "infer":
-        sd = O.init_state_dict(0)
+    if mode in ("infer", "tile"):
         bs = 1
-        x = torch.randn(bs, 2, 256, 256, generator=torch.Generator().manual_seed(1234))
-
-        def step():
-            with torch.inference_mode():
-                O.forward(sd, x, train=False)
+        which, step = cpu_infer_stepper(bs)
         per_step, unit, metric = bs * PATCH_MPIX, "Mpix/s", "ModelB inference Mpix/s"
-        sample = "eval forward of 1 synthetic patch per step (batch 1, like predict.py)"
+        sample = "eval forward of 1 synthetic patch per step (batch 1, the way predict.py:86-103 calls the model)"
     else:
-        kind, alpha, gamma, lr = HYPER[mode]
+        kind = HYPER[mode][0]
         bs = args.ref_batch
-        tr = O.Trainer(O.init_state_dict(0), kind, alpha, gamma, lr)
-        lst, up, ndvi = O.synthetic_batch(bs)
-
-        def step():
-            tr.step(lst, up, ndvi)
+        which, step = cpu_train_stepper(mode, bs)
         per_step, unit, metric = bs, "patches/s", f"ModelB {kind.upper()} train patches/s"
-        sample = f"{kind.upper()} train step on {bs} of the 32 patches per step (bounded CPU sample)"
-    for _ in range(min(args.warmup, 1) if args.warmup else 0):
+        sample = f"one full {kind.upper()} train step on {bs} synthetic patches per step (the benchmark's own batch), torch CPU fp32, all host threads"
+    for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
     val = per_step * args.steps / dt
+    path = ("the reference's own model.py + utils.py (oracle/_ref), train_step order of train_model_B_*.py" if which == "reference"
+            else "PyTorch CPU fp32 (oracle port of model.py + loss helpers)")
     out = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload_name(mode, 32), "reference_path": "PyTorch CPU fp32 (oracle port of model.py + loss helpers)"},
-           "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+           "config": {"workload": workload_name(mode, args.batch), "batch_per_step": bs, "reference_path": path},
+           "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": which, "sample": sample},
            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -156,19 +198,44 @@ def workload_name(mode, batch):
 # --------------------------------------------------------------------------------------------------
 # per-kernel roofline (measured live, CUDA events on the launch stream)
 # --------------------------------------------------------------------------------------------------
-def kernel_rooflines(batch, fp32_peak, tensor_peak_eff):
-    """Times every convolution kernel class on the workload's own 18 layer shapes through the per-op C-ABI, using the
-    same kernel choice as the network plan (tcgen05 where the shape is eligible, fp32 SIMT elsewhere)."""
+def tf32_peak_tflops():
+    """Dense TF32 tensor-core peak of this GPU, measured the way MEASURED_PEAKS.json measures bf16: cuBLAS 8192^3, best of 10, CUDA events."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a, b = torch.randn(n, n, device="cuda"), torch.randn(n, n, device="cuda")
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+LAYERS = [(2, 16, 256), (16, 16, 256), (16, 16, 128), (16, 16, 128), (16, 32, 128), (32, 32, 64), (32, 32, 64), (32, 64, 64),
+          (64, 64, 32), (64, 64, 32), (64, 64, 32), (128, 64, 64), (64, 32, 64), (64, 32, 128), (32, 16, 128), (32, 16, 256),
+          (16, 16, 256), (16, 1, 256)]
+
+
+def kernel_rooflines(batch, fp32_peak, hbm_gbs, bf16_tflops, tf32_tflops, forward_only=False):
+    """Times every convolution kernel class on the workload's own 18 layer shapes through the per-op C-ABI (pre-allocated buffers, CUDA events on
+    the launch stream), with the kernel the network plan picks for each layer.  Per layer the roofline time is
+    max(FLOPs / peak of the unit used, algorithmic bytes / measured HBM bandwidth); a class reports sum(roofline) / sum(measured).
+    Unit peaks: 16-bit 3-term split (FP16 forward, BF16 data gradient) = bf16 / 3; TF32 3-term split (round-1 kernels, weight gradient) =
+    measured TF32 / 3; SIMT = measured FFMA peak.  Algorithmic bytes of a layer: read the input once + write the output once (fp32)."""
     import sifnn_b200
-    from sifnn_b200 import ops
+    from sifnn_b200 import _lib
     lib = sifnn_b200.load()
-    layers = [(2, 16, 256), (16, 16, 256), (16, 16, 128), (16, 16, 128), (16, 32, 128), (32, 32, 64), (32, 32, 64), (32, 64, 64),
-              (64, 64, 32), (64, 64, 32), (64, 64, 32), (128, 64, 64), (64, 32, 64), (64, 32, 128), (32, 16, 128), (32, 16, 256),
-              (16, 16, 256), (16, 1, 256)]
     dev = "cuda"
     use_tc = sifnn_b200.tensor_cores_enabled()
+    st = torch.cuda.current_stream().cuda_stream
 
-    def timed(fn, reps=3):
+    def timed(fn, reps=5):
         fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -180,36 +247,137 @@ def kernel_rooflines(batch, fp32_peak, tensor_peak_eff):
 
     res = {}
 
-    def add(name, t, fl):
-        r = res.setdefault(name, [0.0, 0.0, 0])
-        r[0] += t; r[1] += fl; r[2] += 1
+    def add(name, unit, t, fl, by):
+        peak = {"tensor16": bf16_tflops / 3.0, "tensor32": tf32_tflops / 3.0, "fp32": fp32_peak}[unit]
+        r = res.setdefault(name, {"t": 0.0, "fl": 0.0, "by": 0.0, "roof": 0.0, "roof_c": 0.0, "roof_m": 0.0, "n": 0, "unit": unit, "peak": peak})
+        tc, tm = fl / (peak * 1e12), by / (hbm_gbs * 1e9)
+        r["t"] += t; r["fl"] += fl; r["by"] += by; r["roof"] += max(tc, tm); r["roof_c"] += tc; r["roof_m"] += tm; r["n"] += 1
 
-    for i, (ci, co, hw) in enumerate(layers):
+    for i, (ci, co, hw) in enumerate(LAYERS):
         x = torch.randn(batch, ci, hw, hw, device=dev)
         dy = torch.randn(batch, co, hw, hw, device=dev)
+        y = torch.empty_like(dy)
+        dx = torch.empty_like(x)
         w = torch.randn(co, ci, 3, 3, device=dev) * 0.1
+        dw = torch.empty_like(w)
+        wprep = torch.empty(lib.sifnn_conv3x3_tc_wprep_bytes(max(ci, 8), max(co, 8)) + lib.sifnn_conv3x3_tc_wprep_bytes(max(co, 8), max(ci, 8)) + 2 * ci * co * 12 + 256,
+                            dtype=torch.uint8, device=dev)
+        ws = torch.empty(max(lib.sifnn_conv3x3_wgrad_workspace(batch, ci, co, hw, hw), lib.sifnn_conv3x3_wgrad_tc_workspace(batch, ci, co, hw, hw), 16),
+                         dtype=torch.uint8, device=dev)
         fl = 2.0 * batch * ci * co * 9 * hw * hw
-        if use_tc and co <= 64 and lib.sifnn_conv3x3_tc_supported(ci, co, hw, hw):
-            add("conv3x3_tc_kernel (fwd)", timed(lambda: ops.conv3x3_fwd_tc(x, w)), fl)
+        by = 4.0 * batch * (ci + co) * hw * hw
+        P = lambda t: t.data_ptr()
+        # forward
+        if use_tc and lib.sifnn_conv3x3_fs_supported(ci, co, hw, hw):
+            add("conv3x3_fs_kernel (fwd, FP16 split)", "tensor16", timed(lambda: _lib.call("sifnn_conv3x3_fwd_fs", P(x), None, None, P(w), P(y), None, P(wprep), batch, ci, co, hw, hw, st)), fl, by)
+        elif use_tc and lib.sifnn_conv3x3_ff_supported(ci, co, hw, hw):
+            add("conv3x3_ff_kernel (fwd, FP16 split)", "tensor16", timed(lambda: _lib.call("sifnn_conv3x3_fwd_ff", P(x), None, None, P(w), P(y), None, P(wprep), batch, ci, co, hw, hw, st)), fl, by)
+        elif use_tc and co <= 64 and lib.sifnn_conv3x3_tc_supported(ci, co, hw, hw):
+            add("conv3x3_tc_kernel (fwd, TF32 split, round 1)", "tensor32", timed(lambda: _lib.call("sifnn_conv3x3_fwd_tc", P(x), None, None, P(w), None, P(y), None, P(wprep), batch, ci, co, hw, hw, st)), fl, by)
         else:
-            add("conv3x3_kernel 2->16 + conv3x3_to1_kernel 16->1 (fwd, SIMT)", timed(lambda: ops.conv3x3_fwd(x, w)), fl)
-        if i > 0:
-            if use_tc and lib.sifnn_conv3x3_tc_supported(co, ci, hw, hw):
-                add("conv3x3_tc_kernel (dgrad)", timed(lambda: ops.conv3x3_dgrad_tc(dy, w)), fl)
+            add("conv3x3_kernel 2->16 + conv3x3_to1_kernel 16->1 (fwd, SIMT)", "fp32", timed(lambda: _lib.call("sifnn_conv3x3_fwd", P(x), None, None, P(w), None, P(y), None, batch, ci, co, hw, hw, st)), fl, by)
+        if not forward_only:
+            if i > 0:   # no data gradient for the first layer
+                if use_tc and lib.sifnn_conv3x3_fs_supported(co, ci, hw, hw):
+                    add("conv3x3_fs_kernel (dgrad, BF16 split)", "tensor16", timed(lambda: _lib.call("sifnn_conv3x3_dgrad_fs", P(dy), P(w), P(dx), 0, P(wprep), batch, ci, co, hw, hw, st)), fl, by)
+                elif use_tc and lib.sifnn_conv3x3_ff_supported(co, ci, hw, hw):
+                    add("conv3x3_ff_kernel (dgrad, BF16 split)", "tensor16", timed(lambda: _lib.call("sifnn_conv3x3_dgrad_ff", P(dy), P(w), P(dx), 0, P(wprep), batch, ci, co, hw, hw, st)), fl, by)
+                elif use_tc and lib.sifnn_conv3x3_tc_supported(co, ci, hw, hw):
+                    add("conv3x3_tc_kernel (dgrad, TF32 split, round 1)", "tensor32", timed(lambda: _lib.call("sifnn_conv3x3_dgrad_tc", P(dy), P(w), P(dx), 0, P(wprep), batch, ci, co, hw, hw, st)), fl, by)
+                else:
+                    add("dgrad_from1_kernel 16->1 (dgrad, SIMT)", "fp32", timed(lambda: _lib.call("sifnn_conv3x3_dgrad", P(dy), P(w), P(dx), 0, batch, ci, co, hw, hw, st)), fl, by)
+            if use_tc and lib.sifnn_conv3x3_wgrad_tc_supported(ci, co, hw, hw):
+                add("wgrad_tc_kernel (TF32 split)", "tensor32", timed(lambda: _lib.call("sifnn_conv3x3_wgrad_tc", P(x), None, None, P(dy), P(dw), P(ws), batch, ci, co, hw, hw, st)), fl, by)
             else:
-                add("dgrad_from1_kernel 16->1 (dgrad, SIMT)", timed(lambda: ops.conv3x3_dgrad(dy, w)), fl)
-        if use_tc and lib.sifnn_conv3x3_wgrad_tc_supported(ci, co, hw, hw):
-            add("wgrad_tc_kernel", timed(lambda: ops.conv3x3_wgrad_tc(x, dy)), fl)
-        else:
-            add("wgrad_kernel (SIMT)", timed(lambda: ops.conv3x3_wgrad(x, dy, want_bias=(co == 1))), fl)
-        del x, dy, w
+                db = torch.empty(co, device=dev) if co == 1 else None
+                add("wgrad_kernel (SIMT)", "fp32", timed(lambda: _lib.call("sifnn_conv3x3_wgrad", P(x), None, None, P(dy), P(dw), None if db is None else P(db), P(ws), batch, ci, co, hw, hw, st)), fl, by)
+        del x, dy, y, dx, w, dw, wprep, ws
     out = []
-    for name, (t, fl, n) in res.items():
-        tensor = "tc_kernel" in name
-        peak = tensor_peak_eff if tensor else fp32_peak
-        out.append({"kernel": name, "bound": "tensor" if tensor else "fp32", "launches_per_step": n, "ms_per_step": t * 1e3,
-                    "achieved": fl / t / 1e12, "unit": "TFLOP/s", "peak": peak, "frac": fl / t / 1e12 / peak})
+    for name, r in res.items():
+        hbm_bound = r["roof_m"] > r["roof_c"]
+        out.append({"kernel": name, "bound": "hbm" if hbm_bound else ("tensor" if r["unit"].startswith("tensor") else "fp32"), "launches_per_step": r["n"],
+                    "ms_per_step": r["t"] * 1e3, "achieved_tflops": r["fl"] / r["t"] / 1e12, "achieved_gbs": r["by"] / r["t"] / 1e9,
+                    "unit_peak_tflops": r["peak"], "hbm_peak_gbs": hbm_gbs, "roofline_ms": r["roof"] * 1e3, "frac": r["roof"] / r["t"]})
     return out
+
+
+def timed_events(fn, steps, warm=3):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / steps
+
+
+def sr2_subrecord(model_mod, dev, B, world, rank, devb, nb, steps):
+    """BASELINE.json configs[2]'s loss: the SR2 (gradFTM) training step at the same per-GPU batch, CUDA-graph replay, device time."""
+    import sifnn_b200
+    torch.manual_seed(0)
+    m2 = model_mod.ModelB_2(in_channels=2).to(dev).train()
+    kind, alpha, gamma, lr = HYPER["train_sr2"]
+    tr2 = sifnn_b200.Trainer(m2, kind, alpha, gamma, lr)
+    tr2.broadcast_parameters(0)
+    tr2.capture(*devb[0])
+    dt = timed_events(lambda i: tr2.step_graph(*devb[i % nb]), steps)
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"metric": "ModelB SR2 train patches/s", "value": B * world / float(t[0]), "unit": "patches/s", "ms_per_step": float(t[0]) * 1e3,
+            "batch_per_gpu": B, "global_batch": B * world, "steps": steps, "hyper": {"alpha": alpha, "gamma": gamma, "lr": lr}}
+
+
+def inference_subrecord(m, dev, steps_small=50):
+    """The inference half of the headline metric (BASELINE.json configs[0], [3]): eval forward from the 64x64 LST + 256x256 NDVI patches at
+    batch 1 (predict.py's own call pattern; CUDA-graph replay), 32 and 4096 (chunks of 32 inside the module), device Mpix/s and end to end
+    from pinned host buffers through PipelinedInference, plus the reference's CPU path at batch 1."""
+    import sifnn_b200
+    was = m.training
+    m.eval()
+    rows = []
+    g = torch.Generator().manual_seed(99)
+    for bsz, steps in ((1, steps_small), (32, 10), (4096, 2)):
+        nbuf = 8 if bsz <= 32 else 1   # rotate distinct inputs (at 4096 one batch is 1.1 GB: far beyond L2 anyway)
+        host = [(torch.randn(bsz, 1, 64, 64, generator=g).pin_memory(), torch.randn(bsz, 1, 256, 256, generator=g).pin_memory()) for _ in range(nbuf)]
+        devb = [(l.to(dev), n.to(dev)) for l, n in host]
+        m.enable_eval_graphs(bsz <= 8, max_batch=8)
+
+        def step(i):
+            with torch.inference_mode():
+                return m.forward_from_lowres(*devb[i % nbuf])
+        dt = timed_events(step, steps, warm=2)
+        out_h = [torch.empty((bsz, 1, 256, 256), dtype=torch.float32).pin_memory() for _ in range(2)]
+        pipe = sifnn_b200.PipelinedInference(m)
+        for i in range(2):
+            pipe.submit(*host[i % nbuf], out_h[i % 2])
+        pipe.flush(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            pipe.submit(*host[i % nbuf], out_h[i % 2])
+        pipe.flush(); torch.cuda.synchronize()
+        e2e = (time.perf_counter() - t0) / steps
+        rows.append({"batch": bsz, "mpix_s_device": bsz * PATCH_MPIX / dt, "mpix_s_e2e": bsz * PATCH_MPIX / e2e, "ms_per_batch": dt * 1e3,
+                     "h2d_bytes_per_batch": bsz * (64 * 64 + 256 * 256) * 4, "d2h_bytes_per_batch": bsz * 256 * 256 * 4,
+                     "launch": "cuda-graph replay" if bsz <= 8 else "eager, chunks of 32"})
+        del host, devb, out_h, pipe
+        torch.cuda.empty_cache()
+    m.enable_eval_graphs(False)
+    m.train(was)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    which, cstep = cpu_infer_stepper(1)
+    cstep()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        cstep()
+    cdt = (time.perf_counter() - t0) / 10
+    return {"metric": "ModelB inference Mpix/s", "unit": "Mpix/s", "operand_split": "FP16 3-term (22 significant bits)", "sweep": rows,
+            "cpu_baseline": {"value": PATCH_MPIX / cdt, "unit": "Mpix/s", "cores": cores, "kind": which, "sample": "10 eval forwards of 1 patch after 1 warm-up"}}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -371,58 +539,71 @@ def run_ours(args):
     if rank == 0 and not args.no_roofline:
         from sifnn_b200 import ops
         fp32_peak = ops.fp32_peak_tflops()
-        tensor_eff = bf16 / 2.0 / 3.0  # TF32 dense = half the measured bf16 peak; fp32 parity costs 3 TF32 products per MAC
-        per_kernel = kernel_rooflines(B, fp32_peak, tensor_eff)
-        if mode in ("infer", "tile"):
-            per_kernel = [k for k in per_kernel if "fwd" in k["kernel"]]
+        tf32 = tf32_peak_tflops()
+        per_kernel = kernel_rooflines(B, fp32_peak, hbm, bf16, tf32, forward_only=mode in ("infer", "tile"))
         top = max(per_kernel, key=lambda r: r["ms_per_step"])
         traffic, traffic_source = None, None
-        try:  # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
+        try:  # DRAM bytes of one launch of the dominant kernel class from the committed `ncu --set full` capture (profiles/)
             import csv
-            name = {"wgrad_tc_kernel": "r1l_ncu_full_wgrad_tc_32x16x256_summary.csv",
-                    "wgrad_kernel (SIMT)": "r1i_ncu_full_wgrad_16x16x256_summary.csv",
-                    "conv3x3_tc_kernel (dgrad)": "r1q_ncu_full_conv3x3_tcx_dgrad_16x16x256_summary.csv",
-                    "conv3x3_tc_kernel (fwd)": "r1q_ncu_full_conv3x3_tcx_fwd_32x16x256_summary.csv"}.get(top["kernel"], "r1j_ncu_full_conv3x3_tc_64x32x128_summary.csv")
+            key = top["kernel"].split(" ")[0] + (" dgrad" if "dgrad" in top["kernel"] else (" fwd" if "fwd" in top["kernel"] else ""))
+            name = NCU_SUMMARIES.get(key)
             vals = {r[0]: r[1] for r in csv.reader(open(os.path.join(ROOT, "profiles", name))) if len(r) >= 2}
             traffic = (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e6   # bytes of that one launch
             traffic_source = {"launch": name.replace("_summary.csv", ""), "file": "profiles/" + name,
-                              "metric": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, one launch of the dominant kernel class"}
+                              "metric": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, ONE launch of the dominant kernel class (the layer named in the file)"}
         except Exception:
             pass
-        out["roofline"] = {"bound": top["bound"], "kernel": top["kernel"], "achieved": top["achieved"], "peak": top["peak"], "unit": "TFLOP/s",
+        hbm_bound = top["bound"] == "hbm"
+        out["roofline"] = {"bound": "hbm" if hbm_bound else "tensor", "kernel": top["kernel"],
+                           "achieved": top["achieved_gbs"] if hbm_bound else top["achieved_tflops"],
+                           "peak": hbm if hbm_bound else top["unit_peak_tflops"], "unit": "GB/s" if hbm_bound else "TFLOP/s",
                            "frac": top["frac"], "traffic": traffic, "traffic_source": traffic_source,
-                           "note": "achieved = algorithmic conv FLOPs of the kernel class over the network's 18 layer shapes / CUDA-event time, measured "
-                                   "live through the per-op C-ABI. fp32 peak = this GPU's measured FFMA throughput (sifnn_fp32_peak_kernel, best of 5; not in "
-                                   f"MEASURED_PEAKS.json). tensor peak = {how} bf16 {bf16:.0f} TFLOP/s / 2 (TF32) / 3 (3-term split for fp32 parity) = {tensor_eff:.0f}.",
+                           "peaks": {"hbm_gbs": hbm, "bf16_tflops": bf16, "tf32_tflops_measured_live": tf32, "fp32_ffma_tflops_measured_live": fp32_peak, "source": how},
+                           "note": "dominant = the kernel class with the largest ms_per_step. Per layer, roofline time = max(conv FLOPs / unit peak, (input + output) bytes / "
+                                   "HBM peak); frac = sum of roofline times / sum of CUDA-event times over the class's launches of one step, measured live through the "
+                                   "per-op C-ABI on the network's 18 layer shapes. Unit peaks: 16-bit 3-term split = bf16 / 3, TF32 3-term split = measured TF32 / 3, "
+                                   "SIMT = measured FFMA. For an hbm-bound class achieved / peak are GB/s of algorithmic bytes (frac also counts its compute-bound layers).",
                            "per_kernel": per_kernel}
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        import sifnn_oracle as O
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         if mode in ("infer", "tile"):
-            sd = O.init_state_dict(0)
-            x = torch.randn(1, 2, 256, 256)
-            with torch.inference_mode():
-                O.forward(sd, x)
-                t0 = time.perf_counter()
-                for _ in range(20):
-                    O.forward(sd, x)
-                dt = (time.perf_counter() - t0) / 20
-            out["cpu_baseline"] = {"value": PATCH_MPIX / dt, "unit": unit, "cores": cores, "kind": "port",
+            which, cstep = cpu_infer_stepper(1)
+            cstep()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                cstep()
+            dt = (time.perf_counter() - t0) / 20
+            out["cpu_baseline"] = {"value": PATCH_MPIX / dt, "unit": unit, "cores": cores, "kind": which,
                                    "sample": "20 eval forwards of 1 patch (batch 1, like predict.py), after 1 warm-up"}
         else:
-            kind, alpha, gamma, lr = HYPER[mode]
-            cb = 16
-            ref = O.Trainer(O.init_state_dict(0), kind, alpha, gamma, lr)
-            lst, up, ndvi = O.synthetic_batch(cb)
-            ref.step(lst, up, ndvi)
+            kind = HYPER[mode][0]
+            which, cstep = cpu_train_stepper(mode, B)
+            cstep()
             t0 = time.perf_counter()
-            for _ in range(2):
-                ref.step(lst, up, ndvi)
-            dt = (time.perf_counter() - t0) / 2
-            out["cpu_baseline"] = {"value": cb / dt, "unit": unit, "cores": cores, "kind": "port",
-                                   "sample": f"2 {kind.upper()} train steps of {cb} patches (half a batch) after 1 warm-up, torch CPU fp32"}
+            for _ in range(5):
+                cstep()
+            dt = (time.perf_counter() - t0) / 5
+            out["cpu_baseline"] = {"value": B / dt, "unit": unit, "cores": cores, "kind": which,
+                                   "sample": f"5 full {kind.upper()} train steps of {B} patches (the benchmark's own batch) after 1 warm-up, torch CPU fp32"}
+    ident = None
+    if world > 1 and mode.startswith("train"):
+        # every rank must hold bit-identical weights after the timed steps: all-reduce MIN / MAX of two checksums of the flat parameter buffer
+        flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).double()
+        cs = torch.stack([flat.sum(), (flat * flat).sum()])
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ident = bool(torch.equal(lo, hi))
+    extras = {}
+    if mode == "train_sr1" and not args.no_extras:
+        extras["sr2"] = sr2_subrecord(model_mod, dev, B, world, rank, devb, nb, max(5, args.steps // 2))
+        if world == 1:
+            extras["inference"] = inference_subrecord(m, dev)
     if rank == 0:
+        if ident is not None:
+            out["ranks_identical"] = ident
+        out.update(extras)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -437,10 +618,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="train_sr1", choices=["train_sr1", "train_sr2", "infer", "tile"])
     ap.add_argument("--batch", type=int, default=32, help="patches per GPU per step")
-    ap.add_argument("--ref-batch", type=int, default=8, help="patches per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--ref-batch", type=int, default=32, help="patches per step of the CPU reference arm (default: the benchmark's own batch)")
     ap.add_argument("--no-graph", action="store_true", help="launch the training step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the SR2 and inference sub-records of the default line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

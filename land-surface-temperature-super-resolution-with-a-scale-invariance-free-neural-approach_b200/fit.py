@@ -83,6 +83,35 @@ def _quality_fn(quality):
     return quality
 
 
+def _dp_active() -> bool:
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def reduce_epoch_sums(sums: torch.Tensor, qsum: torch.Tensor, n_batches: int) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """Under data parallelism every rank sees its own shard: sum the per-batch loss / quality sums and the batch counts over the ranks
+    (one small all-reduce per epoch), so that every rank computes the SAME epoch means -- and therefore takes the same early-stopping
+    decision; ranks that disagree on `break` would leave the others hanging in the next gradient all-reduce."""
+    if not _dp_active():
+        return sums, qsum, n_batches
+    import torch.distributed as dist
+    t = torch.cat([sums.reshape(-1).double(), qsum.reshape(-1).double(), torch.tensor([float(n_batches)], dtype=torch.float64, device=sums.device)])
+    dist.all_reduce(t)
+    return t[:sums.numel()].reshape(sums.shape), t[sums.numel():-1].reshape(qsum.shape), int(round(float(t[-1])))
+
+
+def sync_batchnorm_buffers(model, src: int = 0) -> None:
+    """BatchNorm running statistics are per rank (local statistics, like PyTorch DDP, which broadcasts rank 0's buffers before every
+    forward): before evaluating / checkpointing make every rank use rank ``src``'s running_mean / running_var / num_batches_tracked."""
+    if not _dp_active():
+        return
+    import torch.distributed as dist
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            for b in (mod.running_mean, mod.running_var, mod.num_batches_tracked):
+                dist.broadcast(b, src)
+
+
 def _epoch_mean(sums: torch.Tensor, n_batches: int) -> Tuple[float, float, float]:
     ds, pl, loss = (sums / max(n_batches, 1)).cpu().tolist()   # the single device -> host read of the epoch
     return ds, pl, loss
@@ -115,6 +144,7 @@ def train_epoch(trainer: Trainer, batches: Iterable[Batch], device=None,
                 lst_up = bicubic4_cat(lst, ndvi)[:, :1]
             qsum += torch.as_tensor(qf(y, lst_up), dtype=torch.float64, device=dev)
         n += 1
+    sums, qsum, n = reduce_epoch_sums(sums, qsum, n)
     ds, pl, loss = _epoch_mean(sums, n)
     psnr, ssim = ((qsum / max(n, 1)).cpu().tolist() if qf is not None else (float("nan"), float("nan")))
     return ds, pl, loss, psnr, ssim
@@ -142,6 +172,7 @@ def eval_epoch(trainer: Trainer, batches: Iterable[Batch], device=None,
             m.train(was)
             qsum += torch.as_tensor(qf(y, lst_up), dtype=torch.float64, device=dev)
         n += 1
+    sums, qsum, n = reduce_epoch_sums(sums, qsum, n)
     ds, pl, loss = _epoch_mean(sums, n)
     psnr, ssim = ((qsum / max(n, 1)).cpu().tolist() if qf is not None else (float("nan"), float("nan")))
     return ds, pl, loss, psnr, ssim
@@ -151,7 +182,11 @@ def fit(trainer: Trainer, train_batches: Callable[[], Iterable[Batch]], val_batc
         checkpoint: Optional[model_checkpoint] = None, quality=None, on_epoch: Optional[Callable[[int, Dict], None]] = None):
     """The reference's ``train()`` (train_model_B_gradFTM.py:240-354).  ``train_batches`` / ``val_batches`` are callables returning
     a fresh iterable of (lst, lst_up, ndvi) batches per epoch (a DataLoader with shuffle=True is re-iterated the same way).
-    Returns (model, metrics) with the reference's metric names; on early stopping the best state_dict is loaded back."""
+    Returns (model, metrics) with the reference's metric names; on early stopping the best state_dict is loaded back.
+
+    Data parallel (one process per GPU, each loader yielding its own shard): the epoch means are reduced over the ranks and the BatchNorm
+    running buffers of rank 0 are broadcast before every evaluation, so all ranks log the same numbers, make the same early-stopping
+    decision and hold the same state_dict when they checkpoint (the weights themselves are identical by construction)."""
     model = trainer.model
     checkpoint = checkpoint or model_checkpoint(n_epochs, patience=5)
     metrics: Dict[str, object] = {k: [] for k in METRIC_KEYS}
@@ -159,6 +194,7 @@ def fit(trainer: Trainer, train_batches: Callable[[], Iterable[Batch]], val_batc
         dl, pl, tl, tp, ts = train_epoch(trainer, train_batches(), quality=quality)
         for k, v in zip(("train_dsloss", "train_perceploss", "train_loss", "train_psnr", "train_ssim"), (dl, pl, tl, tp, ts)):
             metrics[k].append(v)
+        sync_batchnorm_buffers(model, 0)
         dl, pl, tl, tp, ts = eval_epoch(trainer, val_batches(), quality=quality)
         for k, v in zip(("val_dsloss", "val_perceploss", "val_loss", "val_psnr", "val_ssim"), (dl, pl, tl, tp, ts)):
             metrics[k].append(v)

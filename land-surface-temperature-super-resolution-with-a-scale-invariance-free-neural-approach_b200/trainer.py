@@ -156,11 +156,16 @@ class Trainer:
         return losses
 
     # ------------------------------------------------------------------ CUDA graph replay
-    def capture(self, lst: torch.Tensor, ndvi: torch.Tensor) -> None:
+    def capture(self, lst: torch.Tensor, ndvi: torch.Tensor, single_graph: Optional[bool] = None) -> None:
         """Capture the step for inputs shaped like (lst, ndvi); afterwards ``step_graph`` copies new data into the
-        static buffers and replays.  Single GPU: one graph for the whole step.  Data parallel: three graphs --
-        [input stage, forward, loss, decoder backward] | [encoder backward] | [Adam] -- with the two NCCL bucket
-        all-reduces issued eagerly between them, so the decoder bucket still overlaps the encoder backward."""
+        static buffers and replays.  ONE graph for the whole step, also under data parallelism: the two NCCL bucket
+        all-reduces are captured with the kernels (the decoder bucket on NCCL's stream, overlapping the encoder
+        backward), so the host issues one replay per step.  ``single_graph=False`` (or SIFNN_DP_GRAPHS=3, or a failed
+        capture of the collectives) falls back to three graphs around two eager all-reduces.
+
+        Capturing does NOT change the training state: the two eager warm-up steps it needs (lazy CUDA attributes,
+        allocator, NCCL channels) run on a snapshot of the weights, Adam moments, step counter, BatchNorm running
+        statistics and ``num_batches_tracked``, which is restored before returning."""
         m = self.model
         if not m.training:
             raise SifnnError("Trainer.capture needs model.train()")
@@ -194,7 +199,11 @@ class Trainer:
                       opt["t"].data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world, st["n"], _stream())
 
         segs = [seg_front, seg_adam] if self.world == 1 else [seg_front, seg_encoder, seg_adam]
-        # warm-up outside capture (lazy attribute setup, cudaFuncSetAttribute, allocator) -- two eager steps
+        if single_graph is None:
+            import os
+            single_graph = os.environ.get("SIFNN_DP_GRAPHS", "1") != "3"
+        # warm-up outside capture (lazy attribute setup, cudaFuncSetAttribute, allocator, NCCL channels) -- two eager steps on a snapshot of the state
+        snap = [t.clone() for t in (st["flat"], st["rm"], st["rv"], opt["m"], opt["v"], opt["t"])] + [c.clone() for c in st["counters"]]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -202,19 +211,50 @@ class Trainer:
                 self._replay_or_run(segs, eager=True, fgrad=fgrad, dec=dec)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+
+        def restore():
+            for t, v in zip((st["flat"], st["rm"], st["rv"], opt["m"], opt["v"], opt["t"]), snap):
+                t.copy_(v)
+            for c, v in zip(st["counters"], snap[6:]):
+                c.copy_(v)
+
         n0 = lib.sifnn_launch_count()
-        graphs = []
-        for fn in segs:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fn()
-            graphs.append(g)
+        graphs = None
+        if self.world > 1 and single_graph:
+            try:   # everything, collectives included, in one graph
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ar = BucketedAllReduce(fgrad, dec)
+                    seg_front()
+                    ar.start(0)      # decoder bucket: NCCL's stream forks off the capture stream here and overlaps the encoder backward
+                    seg_encoder()
+                    ar.start(1)
+                    ar.finish()
+                    seg_adam()
+                graphs, self._dp_single = [g], True
+            except Exception as e:   # this NCCL / driver pair cannot capture the collective: three graphs around eager all-reduces
+                import warnings
+                warnings.warn(f"sifnn Trainer.capture: single-graph data-parallel capture failed ({e!r}); using three graphs")
+                torch.cuda.synchronize()
+                n0 = lib.sifnn_launch_count()
+                graphs = None
+        if graphs is None:
+            graphs, self._dp_single = [], False
+            for fn in segs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                graphs.append(g)
         self.graph_launches = int(lib.sifnn_launch_count() - n0)  # kernels of this library inside one replayed step
         self._graph = graphs
         self._segs = segs
         self._ar = (fgrad, dec)
+        restore()
 
     def _replay_or_run(self, segs, eager: bool, fgrad, dec):
+        if not eager and getattr(self, "_dp_single", False):
+            self._graph[0].replay()   # data parallel, collectives captured: one replay per step
+            return
         run = (lambda i: segs[i]()) if eager else (lambda i: self._graph[i].replay())
         if self.world == 1:
             run(0)

@@ -87,6 +87,15 @@ def load_real_pairs(n):
     return np.array(ids), np.stack(lst), np.stack(ndvi)
 
 
+def write_all_real_pairs():
+    """Every real MODIS pair the reference ships (test_data_formatted/data/*_data_dict.pkl, 83 of them) as raw inputs: LST (64,64) in Kelvin,
+    NDVI (256,256).  The oracle is run live on them by tests/test_gpu_fullsize.py, so no outputs are stored.  ~17 MB (fp32 NDVI mantissas do
+    not compress)."""
+    ids, lst, ndvi = load_real_pairs(10 ** 6)
+    np.savez_compressed(os.path.join(OUT, "real_pairs_all.npz"), ids=ids, lst=lst, ndvi=ndvi)
+    print("all real pairs:", ids.shape, lst.shape, ndvi.shape)
+
+
 def ref_step_losses(us, model, kind, lst, lst_up, ndvi, alpha, gamma, loss_fn):
     """The reference train_step body, reference functions only."""
     lst_ndvi = torch.cat((lst_up, ndvi), dim=1)
@@ -138,6 +147,8 @@ def main():
     ids, rl, rn = load_real_pairs(2)
     np.savez_compressed(os.path.join(OUT, "real_pairs.npz"), ids=ids, lst=rl, ndvi=rn)
     print("real pairs", ids, rl.shape, rl.min(), rl.max(), rn.min(), rn.max())
+
+    write_all_real_pairs()
 
     # ---- bicubic: cv2 (reference, utils.py:180) vs torch -------------------------------
     lst, ndvi = synthetic(2)

@@ -48,10 +48,7 @@ def test_loader_feeds_step_host_async(tmp_path, processes):
     ta = Trainer(_model(), "sr1", lr=1e-4)
     first = next(iter(ld))
     assert first[0].is_pinned() and first[2].is_pinned() and first[1] is None
-    sd0 = {k: v.clone() for k, v in ta.model.state_dict().items()}
-    ta.capture(first[0].cuda(), first[2].cuda())        # capture runs warm-up steps: back to the initial state
-    ta.model.load_state_dict(sd0)
-    ta._opt["m"].zero_(); ta._opt["v"].zero_(); ta._opt["t"].zero_()
+    ta.capture(first[0].cuda(), first[2].cuda())        # capture() leaves weights, Adam state and BatchNorm buffers untouched
     ld.epoch = 0
     host_losses = []
     for _ in range(2):

@@ -51,11 +51,7 @@ def _worker(rank, world, port, out):
             mm.load_state_dict(sd)
             mm.cuda().train()
         ta, tb = sifnn_b200.Trainer(ma, "sr2", 0.5, -0.25, 1e-3), sifnn_b200.Trainer(mb, "sr2", 0.5, -0.25, 1e-3)
-        sd0 = {k: v.clone() for k, v in mb.state_dict().items()}
-        tb.capture(sl(lst), sl(ndvi))
-        mb.load_state_dict(sd0)
-        for k in ("m", "v", "t"):
-            tb._opt[k].zero_()
+        tb.capture(sl(lst), sl(ndvi))   # one graph per step, NCCL all-reduces captured; capture() preserves the training state
         for _ in range(2):
             la = ta.step(sl(lst), sl(ndvi))
             lb = tb.step_graph(sl(lst), sl(ndvi)).clone()

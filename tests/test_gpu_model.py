@@ -183,15 +183,17 @@ def test_autograd_dropin_step_vs_golden(kind, tc_mode):
     ref64 = O.Trainer(load_ckpt("1009"), kind, alpha, gamma, lr, dtype=torch.float64)
     ref64.loss_and_grads(*syn_inputs())
     g64 = ref64.flat_grads()
-    off, worst = 0, (0.0, "")
+    off, worst, worst_ratio = 0, (0.0, ""), (0.0, "")
     for name, p in m.named_parameters():
         n = p.numel()
         e_ours = rel_err(p.grad.reshape(-1), g64[off:off + n])
         e_ref = rel_err(g["grads"][off:off + n], g64[off:off + n])
         assert e_ours <= max(1e-4, mult * e_ref), (name, e_ours, e_ref)
         worst = max(worst, (e_ours, name))
+        if e_ours > 1e-4:
+            worst_ratio = max(worst_ratio, (e_ours / e_ref, name))
         off += n
-    print("\nworst per-tensor gradient rel.err vs fp64: %.2e (%s)" % worst)
+    print("\nworst per-tensor gradient rel.err vs fp64: %.2e (%s); largest ours/reference-fp32 ratio among tensors above 1e-4: %.1f (%s)" % (worst + worst_ratio))
     opt.step()
     if "params_after" in g:
         params = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
@@ -275,9 +277,10 @@ def test_graph_replay_matches_eager():
     a, b = make_model(sd=sd).train(), make_model(sd=sd).train()
     ta, tb = sifnn_b200.Trainer(a, "sr1", 0.99, -0.5, 1e-3), sifnn_b200.Trainer(b, "sr1", 0.99, -0.5, 1e-3)
     sd0 = {k: v.clone() for k, v in b.state_dict().items()}
-    tb.capture(lst, ndvi)  # capture runs warm-up steps: restore the initial state afterwards
-    b.load_state_dict(sd0)
-    tb._opt["m"].zero_(); tb._opt["v"].zero_(); tb._opt["t"].zero_()
+    tb.capture(lst, ndvi)  # must leave weights, BatchNorm buffers, counters and Adam state exactly as they were
+    for k, v in b.state_dict().items():
+        assert torch.equal(v, sd0[k]), k
+    assert float(tb._opt["m"].abs().max()) == 0.0 and float(tb._opt["v"].abs().max()) == 0.0 and int(tb._opt["t"]) == 0
     for _ in range(3):
         la = ta.step(lst, ndvi)
         lb = tb.step_graph(lst, ndvi).clone()
@@ -295,10 +298,7 @@ def test_step_host_async_matches_graph_step():
     a, b = make_model(sd=sd).train(), make_model(sd=sd).train()
     ta, tb = sifnn_b200.Trainer(a, "sr2", 0.5, -0.25, 1e-4), sifnn_b200.Trainer(b, "sr2", 0.5, -0.25, 1e-4)
     for t, m in ((ta, a), (tb, b)):
-        sd0 = {k: v.clone() for k, v in m.state_dict().items()}
         t.capture(batches[0][0].cuda(), batches[0][1].cuda())
-        m.load_state_dict(sd0)
-        t._opt["m"].zero_(); t._opt["v"].zero_(); t._opt["t"].zero_()
     outs = [torch.zeros(3, dtype=torch.float64).pin_memory() for _ in range(4)]
     ref = []
     for i, (l, n) in enumerate(batches):
