@@ -100,6 +100,8 @@ int sifnn_conv3x3_dgrad_ff(const float* dy, const float* w, float* dx, int accum
  * wprep: sifnn_conv3x3_tc_wprep_bytes() bytes; the data gradient needs 2 * Cout * 3 * Cin * 4 bytes more (fp32 edge taps). */
 int sifnn_conv3x3_fs_supported(int Cin, int Cout, int H, int W);
 void sifnn_conv3x3_fs_config(int kind, int max_ctas);
+/* also accept 64- and 32-pixel-wide images (M = 64 MMAs, one image row each); off by default: the full-fold kernel is faster there */
+void sifnn_conv3x3_fs_narrow(int on);
 /* debug: device buffer of 16 * 256 uint64 for clock64 stamps of CTA (0,0) per pipeline step (tools/trace_fs.py), or NULL */
 void sifnn_conv3x3_fs_trace(void* buf);
 int sifnn_conv3x3_fwd_fs(const float* in, const float* in_scale, const float* in_shift, const float* w,

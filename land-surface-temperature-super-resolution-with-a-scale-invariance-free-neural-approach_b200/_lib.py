@@ -79,6 +79,7 @@ SIGNATURES = {
     "sifnn_conv3x3_dgrad_ff": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] + [c_int] * 5 + [c_void_p]),
     "sifnn_conv3x3_fs_supported": (c_int, [c_int] * 4),
     "sifnn_conv3x3_fs_config": (None, [c_int, c_int]),
+    "sifnn_conv3x3_fs_narrow": (None, [c_int]),
     "sifnn_conv3x3_fs_trace": (None, [c_void_p]),
     "sifnn_conv3x3_fwd_fs": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
     "sifnn_conv3x3_dgrad_fs": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] + [c_int] * 5 + [c_void_p]),

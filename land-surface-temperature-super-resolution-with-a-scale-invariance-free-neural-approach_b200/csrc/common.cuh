@@ -42,6 +42,18 @@ int conv3x3_fwd_fs_prepped(const float* in, const float* in2, int K1, const floa
                            int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
 int conv3x3_dgrad_fs_prepped(const float* dy, const void* wprep, const float* wedge, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
 
+// "do once per device" (cudaFuncSetAttribute is per device; a process may drive several GPUs, possibly from several threads)
+struct PerDeviceOnce {
+    unsigned long long mask[2] = {0ull, 0ull};   // up to 128 devices
+    bool first_time() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return true;   // unknown device: just do the work again
+        const unsigned long long bit = 1ull << (dev & 63);
+        const unsigned long long old = __atomic_fetch_or(&mask[dev >> 6], bit, __ATOMIC_ACQ_REL);
+        return (old & bit) == 0;
+    }
+};
+
 inline cudaStream_t as_stream(sifnn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __device__ __forceinline__ float warp_sum(float v) {

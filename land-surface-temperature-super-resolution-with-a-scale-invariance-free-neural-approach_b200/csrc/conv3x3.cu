@@ -699,11 +699,10 @@ int launch_conv(const ConvArgs& a0, cudaStream_t st) {
     constexpr int CO_T = CPT * WARPS_CO;
     constexpr int IN_PLANE = (ROWS + 2) * IN_STRIDE;
     constexpr size_t smem = 2 * (size_t)(CI_CHUNK * IN_PLANE + CI_CHUNK * 9 * CO_T) * sizeof(float);  // two pipeline stages
-    static bool attr_done = false;
+    static sifnn::PerDeviceOnce attr_once;   // the attribute is per device: one flag per device, not one per process
     auto kern = conv3x3_kernel<CPT, WARPS_CO, PAD, AFFINE>;
-    if (!attr_done) {
+    if (attr_once.first_time()) {
         SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
     }
     ConvArgs a = a0;
     a.tiles_x = (a.W + TW - 1) / TW;

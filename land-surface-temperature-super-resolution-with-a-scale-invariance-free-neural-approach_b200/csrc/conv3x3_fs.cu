@@ -140,14 +140,14 @@ constexpr float FS_LO_SCALE = 2048.f;   // FP16 split: the residual (and the wei
 
 // one pixel of one chunk: raw fp32 (channel stride FS_PX) -> BatchNorm affine + ReLU -> hi / lo split -> the two 16-byte units of the pixel
 template <int KIND, bool AFFINE>
-__device__ __forceinline__ void fs_convert_pixel(const float* raw, unsigned char* a_hi, int jdst, const float* sc, const float* sh) {
+__device__ __forceinline__ void fs_convert_pixel(const float* raw, int rpx, unsigned char* a_hi, int jdst, const float* sc, const float* sh) {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         if constexpr (KIND != 1) {
             uint32_t hp[4], lp[4];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
-                float t0 = raw[(8 * q + e) * FS_PX], t1 = raw[(8 * q + e + 1) * FS_PX];
+                float t0 = raw[(8 * q + e) * rpx], t1 = raw[(8 * q + e + 1) * rpx];
                 if (AFFINE) {
                     t0 = sifnn::act_affine_relu(t0, sc[8 * q + e], sh[8 * q + e]);
                     t1 = sifnn::act_affine_relu(t1, sc[8 * q + e + 1], sh[8 * q + e + 1]);
@@ -171,7 +171,7 @@ __device__ __forceinline__ void fs_convert_pixel(const float* raw, unsigned char
             float hi[4], lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                float t = raw[(4 * q + e) * FS_PX];
+                float t = raw[(4 * q + e) * rpx];
                 if (AFFINE) t = sifnn::act_affine_relu(t, sc[4 * q + e], sh[4 * q + e]);
                 hi[e] = tf32_hi(t);
                 lo[e] = t - hi[e];
@@ -182,7 +182,7 @@ __device__ __forceinline__ void fs_convert_pixel(const float* raw, unsigned char
     }
 }
 
-template <int KIND, int NG, int PAD, bool AFFINE, bool STATS, bool DBG>
+template <int KIND, int NG, int PAD, bool AFFINE, bool STATS, bool DBG, int MM>
 __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const FsArgs a, const __grid_constant__ CUtensorMap tmap,
                                                                    const __grid_constant__ CUtensorMap tmap2) {
     constexpr int KC = (KIND == 1) ? 8 : 16;
@@ -212,7 +212,10 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = a.H, W = a.W;
-    const int T = W / 128;
+    const int Wt = W < 128 ? W : 128;        // pixels of a row piece (MM = 64 serves the 64- and 32-pixel-wide levels: one image row per MMA, junk rows beyond)
+    const int T = W / Wt;
+    const int rpx = Wt + 8;                    // staged pixels per channel of a raw box: x0 - 4 .. x0 + Wt + 3
+    const uint32_t raw_bytes = (uint32_t)(KC * rpx * 4);
     const int nworkers = gridDim.x;
 
     if (tid == 0) {
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
                 if (rr.wrapped) mbar_wait(raw_empty + rs, rr.phase ^ 1);
                 if (lane == 0) {
                     if (c == 0) FS_STAMP(0, step);
-                    mbar_arrive_expect_tx(raw_full + rs, (uint32_t)L.raw_stage);
+                    mbar_arrive_expect_tx(raw_full + rs, raw_bytes);
                     const int ch = c * KC;
                     unsigned char* dst = raw_s + (size_t)rs * L.raw_stage;
                     if (ch < a.K1) tma_load_3d(dst, &tmap, it.t * 128 - 4, it.r, it.b * a.K1 + ch, raw_full + rs);
@@ -264,8 +267,8 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
         // The tensor pipe executes one of these MMAs per ~111 clocks and its queue is shallow, so every clock this thread spends between two
         // steps is a clock the pipe idles: one thread does everything (no warp-wide polls, no __syncwarp), its waits spin, and the descriptors
         // are advanced by constants instead of being rebuilt.
-        constexpr uint32_t idesc1 = KIND == 0 ? make_idesc_bf16(128, SLOT) : (KIND == 1 ? make_idesc(128, SLOT) : make_idesc_f16(128, SLOT));
-        constexpr uint32_t idesc2 = KIND == 0 ? make_idesc_bf16(128, HALF) : (KIND == 1 ? make_idesc(128, HALF) : make_idesc_f16(128, HALF));
+        constexpr uint32_t idesc1 = KIND == 0 ? make_idesc_bf16(MM, SLOT) : (KIND == 1 ? make_idesc(MM, SLOT) : make_idesc_f16(MM, SLOT));
+        constexpr uint32_t idesc2 = KIND == 0 ? make_idesc_bf16(MM, HALF) : (KIND == 1 ? make_idesc(MM, HALF) : make_idesc_f16(MM, HALF));
         if (lane == 0) {
             mbar_wait_spin(w_full, 0);
             // start-address field = low 14 bits in 16-byte units; every offset below stays inside the 256 KB window, so plain 64-bit adds advance it
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
                 mbar_wait(raw_full + rs, rr.phase);
                 if (p == 0 && c == 0) FS_STAMP(2, step);
                 const float* raw = reinterpret_cast<const float*>(raw_s + (size_t)rs * L.raw_stage) + 4 + p;
-                fs_convert_pixel<KIND, AFFINE>(raw, a_s + (size_t)as * 2 * FS_A_TILE, 4 + p, sc_s + c * KC, sh_s + c * KC);
+                if (p < Wt) fs_convert_pixel<KIND, AFFINE>(raw, rpx, a_s + (size_t)as * 2 * FS_A_TILE, 4 + p, sc_s + c * KC, sh_s + c * KC);
                 fence_proxy_async();           // this thread's st.shared -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(raw_empty + rs); mbar_arrive(a_full + as); }
@@ -343,10 +346,10 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
                 const float* raw = reinterpret_cast<const float*>(raw_s + (size_t)rs * L.raw_stage);
                 if (lane < 2) {
                     // replicate padding: the halo pixel outside the image is a copy of the edge pixel; zero padding: it arrived as zeros
-                    const int jdst = lane == 0 ? 3 : 132;
+                    const int jdst = lane == 0 ? 3 : 4 + Wt;
                     int jsrc = jdst;
-                    if (PAD == 0) { if (lane == 0 && img_l) jsrc = 4; if (lane == 1 && img_r) jsrc = 131; }
-                    fs_convert_pixel<KIND, AFFINE>(raw + jsrc, a_s + (size_t)as * 2 * FS_A_TILE, jdst, sc_s + c * KC, sh_s + c * KC);
+                    if (PAD == 0) { if (lane == 0 && img_l) jsrc = 4; if (lane == 1 && img_r) jsrc = 3 + Wt; }
+                    fs_convert_pixel<KIND, AFFINE>(raw + jsrc, rpx, a_s + (size_t)as * 2 * FS_A_TILE, jdst, sc_s + c * KC, sh_s + c * KC);
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -378,11 +381,11 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
                         const int item = et + i * FS_EDGE_WARPS * 32;
                         const int e = item / HALF, n = item - e * HALF;
                         if (item < ITEMS && (e == 0 ? img_l : img_r)) {
-                            const float* dyp = raw + (e == 0 ? 4 : 131);
+                            const float* dyp = raw + (e == 0 ? 4 : 3 + Wt);
                             const float* we = wedge + ((size_t)e * a.K + c * KC) * HALF + n;
                             float sacc = cacc[i];
 #pragma unroll
-                            for (int k = 0; k < KC; ++k) sacc = fmaf(dyp[k * FS_PX], __ldg(we + (size_t)k * HALF), sacc);
+                            for (int k = 0; k < KC; ++k) sacc = fmaf(dyp[k * rpx], __ldg(we + (size_t)k * HALF), sacc);
                             cacc[i] = sacc;
                         }
                     }
@@ -404,7 +407,9 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
     } else {
         // ======================= epilogue: TMEM -> hi + cross -> rolling ky sums -> global (+ BatchNorm statistics) =======================
         const int quad = warp & 3, half = warp >> 2;
-        const int p = quad * 32 + lane;
+        // M = 128: accumulator row m lives in TMEM lane m.  M = 64: row m lives in lane (m % 16) + 32 * (m / 16), the lower 16 lanes of each quadrant.
+        const int p = (MM == 128) ? quad * 32 + lane : quad * 16 + (lane & 15);
+        const bool px_ok = (MM == 128 || lane < 16) && p < Wt;
         float P0[NG][8], P1[NG][8];
         float s1[STATS ? NG : 1][8], s2[STATS ? NG : 1][8];
 #pragma unroll
@@ -418,8 +423,8 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
         for (int step = 0; step < nsteps; ++step, rc.next()) {
             const int b = it.b, r = it.r, ya = it.ya, yb = it.yb;
             const int x = it.t * 128 + p;
-            const bool emit_prev = (r - 1 >= ya);
-            const bool emit_last = (r == H - 1) && (yb == H);
+            const bool emit_prev = px_ok && (r - 1 >= ya);
+            const bool emit_last = px_ok && (r == H - 1) && (yb == H);
             const int slot = rc.idx;
             if (tid == 0) FS_STAMP(14, step);
             mbar_wait(acc_full + slot, rc.phase);   // suspending wait: the epilogue runs behind the MMAs with five slots of slack, a spin would only take issue slots from the transformers
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
                     if (tid == 0) FS_STAMP(8, step);
                 }
                 if (PAD == 1) {   // column terms of the padding adjoint, computed by the halo warp for this row
-                    if (x == 0 || x == W - 1) {
+                    if (px_ok && (x == 0 || x == W - 1)) {
                         const float* eb = edge_s + (size_t)(step & (FS_ES - 1)) * 2 * HALF + (x == 0 ? 0 : HALF) + g * 16 + half * 8;
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky)
@@ -530,19 +535,27 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
 
 int g_fs_max_ctas = 0;
 unsigned long long* g_fs_trace = nullptr;
+// 64- and 32-pixel-wide levels with M = 64 MMAs (one image row each): OFF by default.  Measured (profiles/r2v_profile_fs_narrow.log): an M = 64
+// MMA costs the tensor core as much as an M = 128 one, so the full-fold kernel, which packs two / four rows into every M = 128 MMA, is faster
+// there (step 4.61 -> 5.02 ms with this path on).  SIFNN_FS_NARROW=1 or sifnn_conv3x3_fs_narrow(1) enables it (tests, A/B runs).
+int g_fs_narrow = -1;
+bool fs_narrow() {
+    if (g_fs_narrow < 0) { const char* e = getenv("SIFNN_FS_NARROW"); g_fs_narrow = (e && e[0] == '1') ? 1 : 0; }
+    return g_fs_narrow == 1;
+}
 bool fs_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SIFNN_FS"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
 
-template <int KIND, int NG, int PAD, bool AFFINE, bool STATS>
+template <int KIND, int NG, int PAD, bool AFFINE, bool STATS, int MM>
 int launch_fs(const FsArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, int gx, int gy, cudaStream_t st) {
     constexpr int KC = (KIND == 1) ? 8 : 16;
     const FsLayout L = fs_layout(a.K / KC, NG, KC, PAD == 1);
-    auto kern = conv3x3_fs_kernel<KIND, NG, PAD, AFFINE, STATS, false>;
+    auto kern = conv3x3_fs_kernel<KIND, NG, PAD, AFFINE, STATS, false, MM>;
     if (a.trace) {
-        if constexpr (PAD == 0 && !AFFINE && !STATS && NG == 1) kern = conv3x3_fs_kernel<KIND, NG, PAD, AFFINE, STATS, true>;   // traced build: plain forward only
+        if constexpr (PAD == 0 && !AFFINE && !STATS && NG == 1 && MM == 128) kern = conv3x3_fs_kernel<KIND, NG, PAD, AFFINE, STATS, true, MM>;   // traced build: plain forward only
     }
     SIFNN_REQUIRE(L.total <= 227 * 1024, "conv3x3_fs: shared-memory budget exceeded (K=%d)", a.K);
     SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
@@ -552,8 +565,12 @@ int launch_fs(const FsArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, i
 
 template <int KIND, int PAD, bool AFFINE, bool STATS>
 int dispatch_fs2(const FsArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, int NG, int gx, int gy, cudaStream_t st) {
-    if (NG == 1) return launch_fs<KIND, 1, PAD, AFFINE, STATS>(a, tm1, tm2, gx, gy, st);
-    return launch_fs<KIND, 2, PAD, AFFINE, STATS>(a, tm1, tm2, gx, gy, st);
+    if (a.W < 128) {   // 64- and 32-pixel-wide levels: M = 64 MMAs, one image row each
+        if (NG == 1) return launch_fs<KIND, 1, PAD, AFFINE, STATS, 64>(a, tm1, tm2, gx, gy, st);
+        return launch_fs<KIND, 2, PAD, AFFINE, STATS, 64>(a, tm1, tm2, gx, gy, st);
+    }
+    if (NG == 1) return launch_fs<KIND, 1, PAD, AFFINE, STATS, 128>(a, tm1, tm2, gx, gy, st);
+    return launch_fs<KIND, 2, PAD, AFFINE, STATS, 128>(a, tm1, tm2, gx, gy, st);
 }
 template <int KIND>
 int dispatch_fs1(int pad, bool affine, bool stats, const FsArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, int NG, int gx, int gy, cudaStream_t st) {
@@ -563,7 +580,7 @@ int dispatch_fs1(int pad, bool affine, bool stats, const FsArgs& a, const CUtens
 }
 
 bool fs_shape_ok(int K, int O, int H, int W) {
-    return (W % 128 == 0) && W >= 128 && W <= 4096 && (K % 16 == 0) && K >= 16 && K <= FS_MAX_K && (O % 16 == 0) && O >= 16 && O <= 128 && (O == 16 || O % 32 == 0) && H >= 1;
+    return ((W % 128 == 0 && W >= 128 && W <= 4096) || ((W == 64 || W == 32) && fs_narrow())) && (K % 16 == 0) && K >= 16 && K <= FS_MAX_K && (O % 16 == 0) && O >= 16 && O <= 128 && (O == 16 || O % 32 == 0) && H >= 1;
 }
 
 int fs_groups(int K, int O, int kind) {   // output groups of 16 channels per CTA
@@ -592,8 +609,9 @@ int run_fs(int pad, const float* in, const float* in2, int K1, const float* in_s
     if (gx > a.nrows) gx = a.nrows;
     if (gx < 1) gx = 1;
     CUtensorMap tm1, tm2;
-    SIFNN_REQUIRE(encode_planes_map(&tm1, in, W, H, (long long)B * a.K1, FS_PX, 1, KC), "conv3x3_fs: cuTensorMapEncodeTiled is unavailable or failed");
-    if (in2) SIFNN_REQUIRE(encode_planes_map(&tm2, in2, W, H, (long long)B * (K - K1), FS_PX, 1, KC), "conv3x3_fs: cuTensorMapEncodeTiled failed (second source)");
+    const int rpx = (W < 128 ? W : 128) + 8;
+    SIFNN_REQUIRE(encode_planes_map(&tm1, in, W, H, (long long)B * a.K1, rpx, 1, KC), "conv3x3_fs: cuTensorMapEncodeTiled is unavailable or failed");
+    if (in2) SIFNN_REQUIRE(encode_planes_map(&tm2, in2, W, H, (long long)B * (K - K1), rpx, 1, KC), "conv3x3_fs: cuTensorMapEncodeTiled failed (second source)");
     else tm2 = tm1;
     const bool affine = in_scale != nullptr;
     SIFNN_REQUIRE(pad == 0 || wedge, "conv3x3_fs: the data-gradient form needs the edge weights");
@@ -691,6 +709,7 @@ int conv3x3_dgrad_fs_prepped(const float* dy, const void* wprep, const float* we
 
 extern "C" void sifnn_conv3x3_fs_config(int kind, int max_ctas) { sifnn::tc_split_set(kind, kind == 2 ? 0 : kind); g_fs_max_ctas = max_ctas; }
 extern "C" void sifnn_conv3x3_fs_trace(void* buf) { g_fs_trace = static_cast<unsigned long long*>(buf); }
+extern "C" void sifnn_conv3x3_fs_narrow(int on) { g_fs_narrow = on ? 1 : 0; }
 extern "C" int sifnn_conv3x3_fs_supported(int Cin, int Cout, int H, int W) { return sifnn::conv3x3_fs_supported(Cin, Cout, H, W) ? 1 : 0; }
 
 extern "C" int sifnn_conv3x3_fwd_fs(const float* in, const float* in_scale, const float* in_shift, const float* w, float* out, double* stats, void* wprep,

@@ -783,10 +783,9 @@ template <int N, int R, int PAD, bool AFFINE, int EW, int WCH, bool BF>
 int launch_tcx_w(const TcArgs& a0, cudaStream_t st) {
     using SM = TcxSmem<N, R, WCH, BF>;
     auto kern = conv3x3_tcx_kernel<N, R, PAD, AFFINE, EW, WCH, BF>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static sifnn::PerDeviceOnce attr_once;   // the attribute is per device: one flag per device, not one per process
+    if (attr_once.first_time()) {
         SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
-        attr_done = true;
     }
     TcArgs a = a0;
     { const char* e = getenv("SIFNN_TC_ABLATE"); a.ablate = e ? atoi(e) : 0; }
@@ -846,10 +845,9 @@ template <int N, int R, int MM, int PAD, bool AFFINE>
 int launch_tc(const TcArgs& a0, cudaStream_t st) {
     using SM = TcSmem<N, R, MM>;
     auto kern = conv3x3_tc_kernel<N, R, MM, PAD, AFFINE>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static sifnn::PerDeviceOnce attr_once;   // the attribute is per device: one flag per device, not one per process
+    if (attr_once.first_time()) {
         SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
-        attr_done = true;
     }
     TcArgs a = a0;
     a.tiles_x = (a.W + MM - 1) / MM;

@@ -52,11 +52,14 @@ int tc_split_kind(int dgrad) {
 }
 void tc_split_set(int fwd_kind, int dgrad_kind) { g_split[0] = fwd_kind; g_split[1] = dgrad_kind; }
 
-int num_sms() {
-    static int n = 0;
+int num_sms() {   // of the CURRENT device (cached per device)
+    static int cache[128] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) dev = 0;
+    int n = __atomic_load_n(&cache[dev], __ATOMIC_RELAXED);
     if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        __atomic_store_n(&cache[dev], n, __ATOMIC_RELAXED);
     }
     return n;
 }

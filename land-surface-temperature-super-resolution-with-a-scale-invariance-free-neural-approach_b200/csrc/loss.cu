@@ -269,11 +269,10 @@ extern "C" int sifnn_loss_fwd_bwd(int kind, const float* sr, const float* ndvi, 
     constexpr int PE1 = 4 * 66 * 66;
     constexpr int PE2 = 72 * 72 + 80 * 72 + 72 * 64;
     constexpr size_t smem = (size_t)(2 * TS * TS + NI * TS + 328 + (PE1 > PE2 ? PE1 : PE2)) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static sifnn::PerDeviceOnce attr_once;   // the attribute is per device: one flag per device, not one per process
+    if (attr_once.first_time()) {
         SIFNN_CUDA(cudaFuncSetAttribute(loss_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SIFNN_CUDA(cudaFuncSetAttribute(loss_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
     }
     dim3 grid((H / T) * (W / T), B);
     if (kind == 1) loss_kernel<1><<<grid, LNT, smem, sifnn::as_stream(stream)>>>(a);

@@ -493,11 +493,10 @@ int launch_wgrad(const WgradArgs& a, const Plan& p, bool affine, cudaStream_t st
     constexpr size_t smem = WGRAD_STAGES * (size_t)(K_CHUNK * (WROWS + 2) * IN_STRIDE + O_CHUNK * WROWS * 32) * sizeof(float);
     auto k_aff = wgrad_kernel<OT, KT, O_CHUNK, K_CHUNK, true, BIAS>;
     auto k_pln = wgrad_kernel<OT, KT, O_CHUNK, K_CHUNK, false, BIAS>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static sifnn::PerDeviceOnce attr_once;   // the attribute is per device: one flag per device, not one per process
+    if (attr_once.first_time()) {
         SIFNN_CUDA(cudaFuncSetAttribute(k_aff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SIFNN_CUDA(cudaFuncSetAttribute(k_pln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
     }
     dim3 grid(p.S, p.k_chunks, p.o_chunks);
     if (affine) k_aff<<<grid, NT, smem, st>>>(a);

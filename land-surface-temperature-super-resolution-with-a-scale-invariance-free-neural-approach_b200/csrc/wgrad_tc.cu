@@ -369,11 +369,10 @@ int launch_wtc(const float* in, const float* dy, WtcArgs a, int& S, bool affine,
     using SM = WtcSmem<KC, N, R, WT>;
     auto k_aff = wgrad_tc_kernel<KC, N, R, WT, true>;
     auto k_pln = wgrad_tc_kernel<KC, N, R, WT, false>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static sifnn::PerDeviceOnce attr_once;   // the attribute is per device: one flag per device, not one per process
+    if (attr_once.first_time()) {
         SIFNN_CUDA(cudaFuncSetAttribute(k_aff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
         SIFNN_CUDA(cudaFuncSetAttribute(k_pln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
-        attr_done = true;
     }
     a.tiles_x = a.W / WT;
     a.tiles_y = (a.H + R - 1) / R;

@@ -25,6 +25,15 @@ def ref_conv(x, w):
     return F.conv2d(F.pad(x.double(), (1, 1, 1, 1), mode="replicate"), w.double())
 
 
+@pytest.fixture(autouse=True)
+def narrow_levels():
+    """The M = 64 path for 64- / 32-pixel-wide images is opt-in (the full-fold kernel is faster there); the tests cover it all the same."""
+    lib = _lib.load()
+    lib.sifnn_conv3x3_fs_narrow(1)
+    yield
+    lib.sifnn_conv3x3_fs_narrow(0)
+
+
 @pytest.fixture(params=[0, 1, 2], ids=["bf16x3", "tf32x3", "fp16x3"])
 def prec(request):
     lib = _lib.load()
@@ -35,7 +44,8 @@ def prec(request):
 
 # (B, Cin, Cout, H, W): one / two / three pieces per row, 1 and 2 output groups per CTA, blockIdx.y > 1, ragged row partitions, single-row images
 SHAPES = [(2, 16, 16, 8, 128), (1, 32, 16, 6, 256), (2, 64, 32, 5, 128), (3, 16, 32, 16, 128), (1, 16, 16, 1, 128), (1, 16, 16, 2, 256),
-          (7, 16, 16, 5, 256), (1, 64, 64, 11, 128), (1, 32, 128, 4, 128), (3, 16, 16, 256, 256), (1, 32, 32, 33, 256), (2, 16, 16, 3, 384)]
+          (7, 16, 16, 5, 256), (1, 64, 64, 11, 128), (1, 32, 128, 4, 128), (3, 16, 16, 256, 256), (1, 32, 32, 33, 256), (2, 16, 16, 3, 384),
+          (2, 32, 32, 64, 64), (3, 64, 32, 7, 64), (4, 64, 64, 32, 32), (5, 32, 64, 3, 32), (2, 16, 16, 1, 32), (1, 64, 128, 11, 64)]   # M = 64 MMAs
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -46,7 +56,8 @@ def test_fs_fwd_plain(shape, prec):
     assert rel_err(y, ref_conv(x, w)) < TOL[prec]
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 16, 8, 128), (1, 32, 16, 6, 256), (2, 64, 32, 9, 128), (2, 16, 32, 40, 128), (1, 64, 64, 6, 256)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 8, 128), (1, 32, 16, 6, 256), (2, 64, 32, 9, 128), (2, 16, 32, 40, 128), (1, 64, 64, 6, 256),
+                                   (2, 32, 32, 64, 64), (3, 64, 64, 32, 32), (2, 64, 32, 6, 64)])
 def test_fs_fwd_affine_stats(shape, prec):
     B, Cin, Cout, H, W = shape
     x, w = rnd(B, Cin, H, W, seed=4), rnd(Cout, Cin, 3, 3, seed=5, scale=0.2)
@@ -61,7 +72,8 @@ def test_fs_fwd_affine_stats(shape, prec):
 
 
 DG_SHAPES = [(2, 16, 16, 8, 128), (1, 16, 32, 6, 256), (2, 64, 32, 5, 128), (1, 32, 64, 4, 128), (2, 32, 16, 7, 256), (1, 16, 16, 1, 128),
-             (2, 32, 16, 150, 256), (1, 128, 64, 5, 128), (2, 16, 16, 3, 384), (3, 64, 64, 4, 128)]
+             (2, 32, 16, 150, 256), (1, 128, 64, 5, 128), (2, 16, 16, 3, 384), (3, 64, 64, 4, 128),
+             (2, 128, 64, 64, 64), (2, 32, 32, 9, 64), (4, 64, 64, 32, 32), (1, 16, 16, 1, 64), (3, 16, 16, 2, 32)]   # M = 64 MMAs
 
 
 @pytest.mark.parametrize("shape", DG_SHAPES)
@@ -85,7 +97,7 @@ def test_fs_long_strips_and_image_crossings(max_ctas):
     try:
         for tf32 in (0, 1, 2):
             lib.sifnn_conv3x3_fs_config(tf32, max_ctas)
-            for (B, Cin, Cout, H, W) in [(3, 16, 16, 100, 256), (3, 32, 32, 37, 128)]:
+            for (B, Cin, Cout, H, W) in [(3, 16, 16, 100, 256), (3, 32, 32, 37, 128), (5, 16, 32, 20, 64), (9, 16, 16, 8, 32)]:
                 x, w = rnd(B, Cin, H, W, seed=21), rnd(Cout, Cin, 3, 3, seed=22, scale=0.2)
                 sc, sh = 1 + 0.3 * rnd(Cin, seed=23), 0.2 * rnd(Cin, seed=24)
                 stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
@@ -104,6 +116,7 @@ def test_fs_long_strips_and_image_crossings(max_ctas):
 
 
 def test_fs_rejects_unsupported():
-    x, w = rnd(1, 16, 8, 64).cuda(), rnd(16, 16, 3, 3).cuda()
-    with pytest.raises(sifnn_b200.SifnnError):
-        ops.conv3x3_fwd_fs(x, w)
+    for shape in ((1, 16, 8, 96), (1, 16, 8, 16), (1, 8, 8, 128)):
+        x, w = rnd(*shape).cuda(), rnd(16, shape[1], 3, 3).cuda()
+        with pytest.raises(sifnn_b200.SifnnError):
+            ops.conv3x3_fwd_fs(x, w)

@@ -60,7 +60,7 @@ def main():
         fl = 2.0 * B * ci * co * 9 * hw * hw
         byts = 4.0 * B * (ci + co) * hw * hw
         floor = max(fl / roof, byts / HBM)
-        if hw % 128 == 0:
+        if lib.sifnn_conv3x3_fs_supported(ci, co, hw, hw):
             fns = {"fwd_fs": lambda: ops.conv3x3_fwd_fs(x, w, sc, sh, stats), "dgrad_fs": lambda: ops.conv3x3_dgrad_fs(dy, w)}
             if a.ff:
                 fns["fwd_ff"] = lambda: ops.conv3x3_fwd_ff(x, w, sc, sh, stats)
