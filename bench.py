@@ -324,6 +324,7 @@ def sr2_subrecord(model_mod, dev, B, world, rank, devb, nb, steps):
     tr2.broadcast_parameters(0)
     tr2.capture(*devb[0])
     dt = timed_events(lambda i: tr2.step_graph(*devb[i % nb]), steps)
+    tr2.release_graphs()   # captured NCCL collectives pin the communicator until their graphs are gone
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
@@ -604,10 +605,20 @@ def run_ours(args):
         if ident is not None:
             out["ranks_identical"] = ident
         out.update(extras)
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        # teardown: the captured graphs hold persistent references on the NCCL communicator (ncclCommDestroy would wait for them), so release them
+        # first; every collective of this run has completed on every rank by now (the checksum / sub-record reductions above were the last ones).
+        sys.stdout.flush()
+        sys.stderr.flush()
+        killer = threading.Timer(30.0, lambda: os._exit(0))   # the result is out: a teardown that hangs must not hang the benchmark
+        killer.daemon = True
+        killer.start()
+        if mode.startswith("train"):
+            tr.release_graphs()
         dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():

@@ -251,6 +251,19 @@ class Trainer:
         self._ar = (fgrad, dec)
         restore()
 
+    def release_graphs(self) -> None:
+        """Drop the captured CUDA graphs (and the host-copy pipeline).  REQUIRED before ``torch.distributed.destroy_process_group()`` when the
+        data-parallel step was captured as one graph: NCCL counts every captured collective as a persistent reference on its communicator and
+        ``ncclCommDestroy`` waits until the graphs that hold them are gone -- a live graph makes the teardown hang."""
+        import gc
+        torch.cuda.synchronize()
+        self._graph = None
+        self._segs = None
+        self._dp_single = False
+        self._host_pipe = None
+        gc.collect()
+        torch.cuda.synchronize()
+
     def _replay_or_run(self, segs, eager: bool, fgrad, dec):
         if not eager and getattr(self, "_dp_single", False):
             self._graph[0].replay()   # data parallel, collectives captured: one replay per step

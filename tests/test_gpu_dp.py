@@ -59,6 +59,8 @@ def _worker(rank, world, port, out):
         pb = torch.cat([p.detach().reshape(-1) for p in mb.parameters()])
         assert torch.allclose(la, lb, rtol=1e-6), (la, lb)
         assert float((pa - pb).abs().max()) <= 1e-6 * float(pa.abs().max()), float((pa - pb).abs().max())
+        assert getattr(tb, "_dp_single", False), "the data-parallel step should replay as ONE graph with the all-reduces captured"
+        tb.release_graphs()   # captured collectives pin the NCCL communicator: drop the graphs before destroy_process_group()
     finally:
         dist.destroy_process_group()
 
