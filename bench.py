@@ -262,7 +262,8 @@ def kernel_rooflines(batch, fp32_peak, hbm_gbs, bf16_tflops, tf32_tflops, forwar
         dw = torch.empty_like(w)
         wprep = torch.empty(lib.sifnn_conv3x3_tc_wprep_bytes(max(ci, 8), max(co, 8)) + lib.sifnn_conv3x3_tc_wprep_bytes(max(co, 8), max(ci, 8)) + 2 * ci * co * 12 + 256,
                             dtype=torch.uint8, device=dev)
-        ws = torch.empty(max(lib.sifnn_conv3x3_wgrad_workspace(batch, ci, co, hw, hw), lib.sifnn_conv3x3_wgrad_tc_workspace(batch, ci, co, hw, hw), 16),
+        ws = torch.empty(max(lib.sifnn_conv3x3_wgrad_workspace(batch, ci, co, hw, hw), lib.sifnn_conv3x3_wgrad_tc_workspace(batch, ci, co, hw, hw),
+                             lib.sifnn_conv3x3_wgrad_km_workspace(batch, ci, co, hw, hw), 16),
                          dtype=torch.uint8, device=dev)
         fl = 2.0 * batch * ci * co * 9 * hw * hw
         by = 4.0 * batch * (ci + co) * hw * hw
@@ -286,7 +287,9 @@ def kernel_rooflines(batch, fp32_peak, hbm_gbs, bf16_tflops, tf32_tflops, forwar
                     add("conv3x3_tc_kernel (dgrad, TF32 split, round 1)", "tensor32", timed(lambda: _lib.call("sifnn_conv3x3_dgrad_tc", P(dy), P(w), P(dx), 0, P(wprep), batch, ci, co, hw, hw, st)), fl, by)
                 else:
                     add("dgrad_from1_kernel 16->1 (dgrad, SIMT)", "fp32", timed(lambda: _lib.call("sifnn_conv3x3_dgrad", P(dy), P(w), P(dx), 0, batch, ci, co, hw, hw, st)), fl, by)
-            if use_tc and lib.sifnn_conv3x3_wgrad_tc_supported(ci, co, hw, hw):
+            if use_tc and co > 1 and not (ci >= 64 and hw >= 64) and lib.sifnn_conv3x3_wgrad_km_supported(ci, co, hw, hw):   # the plan's rule (modelb.cu wgrad)
+                add("wgrad_km_kernel (BF16 split)", "tensor16", timed(lambda: _lib.call("sifnn_conv3x3_wgrad_km", P(x), None, None, P(dy), P(dw), P(ws), batch, ci, co, hw, hw, st)), fl, by)
+            elif use_tc and lib.sifnn_conv3x3_wgrad_tc_supported(ci, co, hw, hw):
                 add("wgrad_tc_kernel (TF32 split)", "tensor32", timed(lambda: _lib.call("sifnn_conv3x3_wgrad_tc", P(x), None, None, P(dy), P(dw), P(ws), batch, ci, co, hw, hw, st)), fl, by)
             else:
                 db = torch.empty(co, device=dev) if co == 1 else None

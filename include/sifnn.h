@@ -127,6 +127,18 @@ int sifnn_conv3x3_wgrad_tc(const float* in, const float* in_scale, const float* 
                            const float* dy, float* dw, void* workspace,
                            int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
 
+/* Weight gradient with 16-bit K-major operands (csrc/wgrad_km.cu, round 2): 16 pixels per MMA, all nine taps and all hi/lo products in ONE MMA per
+ * K step (M = 3 input rows x hi/lo x channels, N = 3 column-shifted dy copies x hi/lo x channels); activations split in FP16 (22 significant bits), gradients
+ * in BF16 (16 bits, fp32 exponent range).  Same result contract as sifnn_conv3x3_wgrad_tc.  Shapes: Cin, Cout = 16 or a multiple of 32 (up to 256),
+ * W a multiple of 32, H a multiple of 8 / 4 / 2 (rows per tile).  workspace: sifnn_conv3x3_wgrad_km_workspace() bytes.
+ * sifnn_conv3x3_wgrad_km_config(fmt_x, fmt_dy): 0 = FP16, 1 = BF16 per operand (defaults 0, 1). */
+int sifnn_conv3x3_wgrad_km_supported(int Cin, int Cout, int H, int W);
+size_t sifnn_conv3x3_wgrad_km_workspace(int B, int Cin, int Cout, int H, int W);
+void sifnn_conv3x3_wgrad_km_config(int fmt_x, int fmt_dy);
+int sifnn_conv3x3_wgrad_km(const float* in, const float* in_scale, const float* in_shift,
+                           const float* dy, float* dw, void* workspace,
+                           int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
+
 /* Train-time quality metrics on the device (utils.py:548-578 psnr_skimage / ssim_skimage, called every step at
  * train_model_B_gradFTM.py:126-127 after two device->host copies): out2[0] = mean PSNR, out2[1] = mean SSIM
  * (skimage defaults: 7x7 uniform window, sample covariance, K1 .01, K2 .03) of pred against target, both (B,1,H,W),

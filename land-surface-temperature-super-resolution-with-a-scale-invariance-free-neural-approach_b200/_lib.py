@@ -14,7 +14,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libsifnn_b200.so")
-SOURCES = ["core.cu", "conv3x3.cu", "conv3x3_tc.cu", "conv3x3_ff.cu", "conv3x3_fs.cu", "wgrad.cu", "wgrad_tc.cu", "elementwise.cu", "loss.cu", "quality.cu", "adam.cu", "modelb.cu"]
+SOURCES = ["core.cu", "conv3x3.cu", "conv3x3_tc.cu", "conv3x3_ff.cu", "conv3x3_fs.cu", "wgrad.cu", "wgrad_tc.cu", "wgrad_km.cu", "elementwise.cu", "loss.cu", "quality.cu", "adam.cu", "modelb.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared"]
 
@@ -89,6 +89,10 @@ SIGNATURES = {
     "sifnn_conv3x3_wgrad_tc_supported": (c_int, [c_int] * 4),
     "sifnn_conv3x3_wgrad_tc_workspace": (c_size_t, [c_int] * 5),
     "sifnn_conv3x3_wgrad_tc": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
+    "sifnn_conv3x3_wgrad_km_supported": (c_int, [c_int] * 4),
+    "sifnn_conv3x3_wgrad_km_workspace": (c_size_t, [c_int] * 5),
+    "sifnn_conv3x3_wgrad_km_config": (None, [c_int, c_int]),
+    "sifnn_conv3x3_wgrad_km": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
     "sifnn_bn_train_finalize": (c_int, [c_void_p] * 9 + [c_int, c_double, c_void_p]),
     "sifnn_bn_eval_affine": (c_int, [c_void_p] * 6 + [c_int, c_void_p]),
     "sifnn_bn_relu_bwd_reduce": (c_int, [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),

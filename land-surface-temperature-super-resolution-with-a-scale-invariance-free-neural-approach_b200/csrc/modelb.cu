@@ -146,8 +146,10 @@ Workspace carve(const Net& n, void* base, int B, int H, int W, int train) {
             const int s = n.conv[i].level;
             const size_t b = sifnn_conv3x3_wgrad_workspace(B, n.conv[i].cin, n.conv[i].cout, H >> s, W >> s);
             const size_t b2 = sifnn_conv3x3_wgrad_tc_workspace(B, n.conv[i].cin, n.conv[i].cout, H >> s, W >> s);
+            const size_t b3 = sifnn_conv3x3_wgrad_km_workspace(B, n.conv[i].cin, n.conv[i].cout, H >> s, W >> s);
             if (b > mx) mx = b;
             if (b2 > mx) mx = b2;
+            if (b3 > mx) mx = b3;
         }
         w.wgrad_ws = c.take<char>(mx);
     }
@@ -321,6 +323,12 @@ extern "C" int sifnn_modelb_backward(const sifnn_modelb_cfg* cfg, const float* p
     // gradient of conv i's weights; input = raw[aff] through BN+ReLU, or a plain tensor
     auto wgrad = [&](int i, const float* in, int aff, const float* g) -> int {
         const ConvDesc& c = n.conv[i];
+        // 16-bit K-major kernel (wgrad_km.cu) except for wide inputs on large images, where the TF32 kernel's bigger channel blocks win
+        // (profiles/r2w_profile_wgrad.log: 64->32 @128 and 128->64 @64 are 4-10 % faster on wgrad_tc, everything else 1.0-2.1x faster on km)
+        const bool km_wins = !(c.cin >= 64 && ws[c.level] >= 64);
+        if (tc_enabled() && i != 17 && km_wins && sifnn_conv3x3_wgrad_km_supported(c.cin, c.cout, hs[c.level], ws[c.level]))
+            return sifnn_conv3x3_wgrad_km(in, aff >= 0 ? sc(aff) : nullptr, aff >= 0 ? sh(aff) : nullptr, g, grads + n.w_off[i], w.wgrad_ws, B, c.cin,
+                                          c.cout, hs[c.level], ws[c.level], stream);
         if (tc_enabled() && i != 17 && sifnn_conv3x3_wgrad_tc_supported(c.cin, c.cout, hs[c.level], ws[c.level]))
             return sifnn_conv3x3_wgrad_tc(in, aff >= 0 ? sc(aff) : nullptr, aff >= 0 ? sh(aff) : nullptr, g, grads + n.w_off[i], w.wgrad_ws, B, c.cin,
                                           c.cout, hs[c.level], ws[c.level], stream);

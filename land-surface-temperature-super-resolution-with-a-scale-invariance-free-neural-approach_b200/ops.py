@@ -160,6 +160,20 @@ def conv3x3_wgrad_tc(x, dy, in_scale=None, in_shift=None):
     return dw
 
 
+def conv3x3_wgrad_km(x, dy, in_scale=None, in_shift=None):
+    """Weight gradient with 16-bit K-major operands (csrc/wgrad_km.cu); same result contract as conv3x3_wgrad."""
+    _chk(x, dy, in_scale, in_shift)
+    B, Cin, H, W = x.shape
+    Cout = dy.shape[1]
+    lib = _lib.load()
+    if not lib.sifnn_conv3x3_wgrad_km_supported(Cin, Cout, H, W):
+        raise _lib.SifnnError(f"conv3x3_wgrad_km: unsupported shape Cin={Cin} Cout={Cout} H={H} W={W}")
+    ws = torch.empty(max(lib.sifnn_conv3x3_wgrad_km_workspace(B, Cin, Cout, H, W), 16), dtype=torch.uint8, device=x.device)
+    dw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
+    _lib.call("sifnn_conv3x3_wgrad_km", _p(x), _p(in_scale), _p(in_shift), _p(dy), _p(dw), _p(ws), B, Cin, Cout, H, W, _s())
+    return dw
+
+
 def bn_train_finalize(stats, gamma, beta, n: float, running_mean=None, running_var=None):
     _chk(stats, gamma, beta, running_mean, running_var)
     C = gamma.numel()
