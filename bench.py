@@ -184,7 +184,7 @@ def run_reference(args):
            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": which, "sample": sample},
            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 def workload_name(mode, batch):
@@ -220,6 +220,16 @@ def tf32_peak_tflops():
 LAYERS = [(2, 16, 256), (16, 16, 256), (16, 16, 128), (16, 16, 128), (16, 32, 128), (32, 32, 64), (32, 32, 64), (32, 64, 64),
           (64, 64, 32), (64, 64, 32), (64, 64, 32), (128, 64, 64), (64, 32, 64), (64, 32, 128), (32, 16, 128), (32, 16, 256),
           (16, 16, 256), (16, 1, 256)]
+
+
+_RESULT_OUT = None
+
+
+def emit(record):
+    """The one JSON line, on the process's original stdout (see main)."""
+    f = _RESULT_OUT or sys.stdout
+    f.write(json.dumps(record) + "\n")
+    f.flush()
 
 
 def kernel_rooflines(batch, fp32_peak, hbm_gbs, bf16_tflops, tf32_tflops, forward_only=False):
@@ -608,7 +618,7 @@ def run_ours(args):
         if ident is not None:
             out["ranks_identical"] = ident
         out.update(extras)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         # teardown: the captured graphs hold persistent references on the NCCL communicator (ncclCommDestroy would wait for them), so release them
         # first; every collective of this run has completed on every rank by now (the checksum / sub-record reductions above were the last ones).
@@ -638,6 +648,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the SR2 and inference sub-records of the default line")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON record): anything a library writes to file descriptor 1 on the way (NCCL prints its version banner
+    # there when NCCL_DEBUG=VERSION is set on the box) goes to stderr instead
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

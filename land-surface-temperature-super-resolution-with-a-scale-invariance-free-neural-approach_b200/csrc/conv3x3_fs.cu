@@ -15,13 +15,14 @@
 // so the epilogue is TMEM load -> hi + cross -> two adds -> store: no shuffles, no inter-warp exchange, no barrier, no tile carries.
 // Padding: replicate = the halo pixel is a copy of the edge pixel (columns) / the rolling-sum edge rule (rows).  Data gradient: zero halo
 // (TMA zero fill) + the adjoint of the replicate padding: rows by the rolling-sum rule (own opposite tap), columns by a correction
-// C[ky][o] = sum_c dy[edge pixel][c] * wf[c][o][ky][opposite kx] that one warp computes in fp32 per row and the edge lane adds -- no
+// C[ky][o] = sum_c dy[edge pixel][c] * wf[c][o][ky][opposite kx] that the edge warps (or the transformer threads) compute in fp32 per row and the edge lane adds -- no
 // border pass, no extra MMAs.
 // Two output groups (32 channels) share one MMA pair (N = 192 / 96) when the layer has >= 32 output channels; more go to blockIdx.y.
 //
-// Warp roles (16 warps, 18 for the data gradient): 0..7 epilogue (TMEM lane quadrant = warp % 4, channel half = warp / 4), 8 TMA loader,
+// Warp roles (16 warps): 0..7 epilogue (TMEM lane quadrant = warp % 4, channel half = warp / 4), 8 TMA loader,
 // 9 and 15 MMA issuers (even / odd steps: the per-step bookkeeping of one overlaps the MMAs of the other), 10..13 transformers
-// (thread = pixel), 14 halo pixels, 16..17 column terms of the padding adjoint (data gradient).
+// (thread = pixel), 14 halo pixels.  Data gradient, column terms of the padding adjoint: + warps 16, 17 (one output group), or the
+// transformer threads after their pixel (two groups; see fs_edge_warps).
 #include "tc_common.cuh"
 
 #include <cstdlib>
@@ -32,8 +33,39 @@ namespace {
 using namespace sifnn_tc;
 
 constexpr int FS_EPI_WARPS = 8, FS_LOAD_WARP = 8, FS_MMA_WARP = 9, FS_XF_WARP0 = 10, FS_XF_WARPS = 4, FS_HALO_WARP = 14, FS_MMA_WARP2 = 15;
-constexpr int FS_EDGE_WARP0 = 16, FS_EDGE_WARPS = 2;   // data gradient only
-__host__ __device__ constexpr int fs_threads(int pad) { return (pad == 1 ? FS_EDGE_WARP0 + FS_EDGE_WARPS : FS_EDGE_WARP0) * 32; }
+// Data gradient: who computes the column terms of the padding adjoint.  One output group: two extra warps, 16 and 17 (18 warps = five per
+// scheduler = a 96-register cap, which that epilogue fits).  Two output groups: the epilogue needs ~120 registers (at 96 it spilled: 2600
+// instead of 1500 clocks per step), so the CTA stays at 16 warps and the transformer threads take one or two terms each after their pixel.
+// Measured (profiles/r2z_fs_dgrad_edge_variants.log, us, layers 16->16@256 / 32->16@256 / 16->32@256 / 32->32@128 / 64->32@128):
+//   two extra warps everywhere 88 / 220 / 135 /  97 / 162;   transformer threads everywhere 96 / 143 / 156 / 67 / 115;
+//   halo warp 105 / 139 / 173 / 74 / 132;   one warp instead of the second MMA issuer (two groups) - / 152 / - / 115 / 214.
+__host__ __device__ constexpr int fs_edge_warps(int pad, int ng) { return (pad == 1 && ng == 1) ? 2 : 0; }
+constexpr int FS_EDGE_WARP0 = 16;
+__host__ __device__ constexpr int fs_threads(int pad, int ng) { return (16 + fs_edge_warps(pad, ng)) * 32; }
+
+// One chunk of the column terms: C[e][n] += sum_k dy[edge pixel e][k] * wf[e][k][n] for this thread's items (item = e * HALF + n, dealt round-robin
+// to NT threads); after the last chunk the sums go to the edge row `eb` that the epilogue's edge lanes add.
+template <int KC, int HALF, int NT, int PER>
+__device__ __forceinline__ void fs_edge_chunk(float (&cacc)[PER], int et, int nitems, int ebase, const float* raw0, const float* wedge_s, int K, int c, int rpx,
+                                              int Wt, bool last, float* eb) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        if (et + i * NT < nitems) {
+            const int item = ebase + et + i * NT;
+            const float* dyp = raw0 + (item < HALF ? 4 : 3 + Wt);
+            const float* we = wedge_s + (size_t)(item < HALF ? 0 : K - 1) * HALF + (size_t)c * KC * HALF + item;   // [e][k][n]
+            float dv[KC], wv[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) { dv[k] = dyp[k * rpx]; wv[k] = we[k * HALF]; }
+            float s0 = cacc[i], s1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < KC; k += 2) { s0 = fmaf(dv[k], wv[k], s0); s1 = fmaf(dv[k + 1], wv[k + 1], s1); }
+            float sacc = s0 + s1;
+            if (last) { eb[item] = sacc; sacc = 0.f; }
+            cacc[i] = sacc;
+        }
+    }
+}
 constexpr int FS_PX = 136;                 // staged pixels of a row piece: x0 - 4 .. x0 + 131 (16-byte aligned both ends); MMA row m of view kx = pixel index 3 + kx + m
 constexpr int FS_A_TILE = 2 * FS_PX * 16;  // bytes of one (hi or lo) activation tile of a chunk: [2 q][136 pixels][16 B]
 constexpr int FS_MAX_K = 64;               // input channels per launch
@@ -42,6 +74,7 @@ constexpr int FS_ES = 16;                  // ring of edge-correction rows (the 
 #define FS_STAMP(ev, idx) do { if (DBG && a.trace && blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 256) a.trace[(ev) * 256 + (idx)] = clock64(); } while (0)
 
 struct FsArgs {
+    int ablate;   // timing experiments only (SIFNN_FS_ABLATE): 1 skip the edge-column math, 2 skip the global stores, 4 skip the accumulate loads
     const float* in_scale;
     const float* in_shift;
     const unsigned char* wprep;   // [gridDim.y][chunk][kx][2 q][(s, ky, g, o) = 96 NG rows][16 B]
@@ -56,7 +89,7 @@ struct FsArgs {
 };
 
 struct FsLayout {
-    int edge, stat, w, a, raw, total;
+    int edge, wedge, stat, w, a, raw, total;
     int AS, RS, raw_stage;
 };
 __host__ __device__ inline FsLayout fs_layout(int nchunks, int NG, int KC, bool pad1) {
@@ -64,6 +97,7 @@ __host__ __device__ inline FsLayout fs_layout(int nchunks, int NG, int KC, bool 
     int off = 1024;               // [0, 1024): mbarriers + TMEM slot
     off += 2 * FS_MAX_K * 4;      // BatchNorm scale / shift of the input channels
     L.edge = off; if (pad1) off += FS_ES * 2 * 48 * NG * 4;
+    L.wedge = off; if (pad1) off += 2 * nchunks * KC * 48 * NG * 4;   // fp32 weights of the column terms of the padding adjoint (data gradient)
     L.stat = off; if (!pad1) off += 4 * 2 * 16 * NG * 4;   // per-quadrant partial BatchNorm sums of the CTA
     off = (off + 1023) & ~1023;
     L.w = off; off += nchunks * 3 * 2 * 96 * NG * 16;
@@ -183,10 +217,12 @@ __device__ __forceinline__ void fs_convert_pixel(const float* raw, int rpx, unsi
 }
 
 template <int KIND, int NG, int PAD, bool AFFINE, bool STATS, bool DBG, int MM>
-__global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const FsArgs a, const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(fs_threads(PAD, NG), 1) conv3x3_fs_kernel(const FsArgs a, const __grid_constant__ CUtensorMap tmap,
                                                                    const __grid_constant__ CUtensorMap tmap2) {
     constexpr int KC = (KIND == 1) ? 8 : 16;
-    constexpr int NPROD = FS_XF_WARPS + 1 + (PAD == 1 ? FS_EDGE_WARPS : 0);   // warps that read a raw stage and arrive on the operand barrier
+    constexpr int EDGE_WARPS = fs_edge_warps(PAD, NG), EDGE_WARP0 = FS_EDGE_WARP0;
+    constexpr bool EDGE_IN_XF = (PAD == 1 && NG == 2);
+    constexpr int NPROD = FS_XF_WARPS + 1 + EDGE_WARPS;   // warps that read a raw stage and arrive on the operand barrier
     constexpr int NSLOT = (NG == 1) ? 5 : 2;     // TMEM ring: 96 NG columns per row piece
     constexpr int SLOT = 96 * NG, HALF = 48 * NG;
     constexpr int W_TILE = 2 * SLOT * 16;        // bytes of the weight tile of one (chunk, kx)
@@ -205,6 +241,7 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
     float* sc_s = reinterpret_cast<float*>(smem + 1024);
     float* sh_s = sc_s + FS_MAX_K;
     float* edge_s = reinterpret_cast<float*>(smem + L.edge);   // [FS_ES][2 edges][48 NG]
+    float* wedge_s = reinterpret_cast<float*>(smem + L.wedge); // [2 edges][K][48 NG]
     unsigned char* w_s = smem + L.w;
     unsigned char* a_s = smem + L.a;
     unsigned char* raw_s = smem + L.raw;
@@ -226,8 +263,12 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
         fence_mbar_init();
     }
     if (warp == FS_MMA_WARP) tmem_alloc(tmem_slot, 512);
+    if (PAD == 1) {   // resident: with ~200 KB of shared memory there is next to no L1 left and every __ldg of these weights was an L2 round trip
+        const float* wg = a.wedge + (size_t)blockIdx.y * 2 * a.K * HALF;
+        for (int i = tid; i < 2 * a.K * HALF; i += fs_threads(PAD, NG)) wedge_s[i] = __ldg(wg + i);
+    }
     if (AFFINE) {
-        for (int i = tid; i < a.K; i += fs_threads(PAD)) { sc_s[i] = a.in_scale ? __ldg(a.in_scale + i) : 1.f; sh_s[i] = a.in_shift ? __ldg(a.in_shift + i) : 0.f; }
+        for (int i = tid; i < a.K; i += fs_threads(PAD, NG)) { sc_s[i] = a.in_scale ? __ldg(a.in_scale + i) : 1.f; sh_s[i] = a.in_shift ? __ldg(a.in_shift + i) : 0.f; }
     }
     tc_fence_before();
     __syncthreads();
@@ -315,10 +356,17 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
         }
         __syncwarp();
     } else if (warp >= FS_XF_WARP0 && warp < FS_HALO_WARP) {
-        // ======================= transformers: thread = pixel x0 + p =======================
+        // ======================= transformers: thread = pixel x0 + p (+ column terms of the padding adjoint, two-group data gradient) =======================
         const int p = tid - FS_XF_WARP0 * 32;
+        float cacc[2] = {0.f, 0.f};
         FsRing rr(RS), ra(AS);
         for (int step = 0; step < nsteps; ++step) {
+            int nitems = 0, ebase = 0;
+            if (EDGE_IN_XF && !(a.ablate & 1)) {
+                const bool img_l = (it.t == 0), img_r = (it.t == T - 1);
+                if (img_l && img_r) nitems = 2 * HALF;
+                else if (img_l || img_r) { nitems = HALF; ebase = img_l ? 0 : HALF; }
+            }
             for (int c = 0; c < nchunks; ++c, rr.next(), ra.next()) {
                 const int rs = rr.idx, as = ra.idx;
                 if (p == 0 && c == 0) FS_STAMP(13, step);
@@ -326,13 +374,17 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
                 if (p == 0 && c == 0) FS_STAMP(1, step);
                 mbar_wait(raw_full + rs, rr.phase);
                 if (p == 0 && c == 0) FS_STAMP(2, step);
-                const float* raw = reinterpret_cast<const float*>(raw_s + (size_t)rs * L.raw_stage) + 4 + p;
-                if (p < Wt) fs_convert_pixel<KIND, AFFINE>(raw, rpx, a_s + (size_t)as * 2 * FS_A_TILE, 4 + p, sc_s + c * KC, sh_s + c * KC);
+                const float* raw0 = reinterpret_cast<const float*>(raw_s + (size_t)rs * L.raw_stage);
+                if (p < Wt) fs_convert_pixel<KIND, AFFINE>(raw0 + 4 + p, rpx, a_s + (size_t)as * 2 * FS_A_TILE, 4 + p, sc_s + c * KC, sh_s + c * KC);
+                if (EDGE_IN_XF)
+                    fs_edge_chunk<KC, HALF, FS_XF_WARPS * 32, 2>(cacc, p, nitems, ebase, raw0, wedge_s, a.K, c, rpx, Wt, c == nchunks - 1,
+                                                                 edge_s + (size_t)(step & (FS_ES - 1)) * 2 * HALF);
                 fence_proxy_async();           // this thread's st.shared -> visible to the tensor core (async proxy)
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(raw_empty + rs); mbar_arrive(a_full + as); }
+                if (lane == 0) { mbar_arrive(raw_empty + rs); mbar_arrive(a_full + as); }   // (the edge row is published before the MMAs of this step may start)
                 if (p == 0 && c == nchunks - 1) FS_STAMP(3, step);
             }
+            if (EDGE_IN_XF) it.next();
         }
     } else if (warp == FS_HALO_WARP) {
         // ======================= halo pixels: lanes 0 and 1 convert pixel x0 - 1 and x0 + 128 =======================
@@ -357,50 +409,34 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
             }
             it.next();
         }
-    } else if (PAD == 1 && warp >= FS_EDGE_WARP0) {
+    } else if (PAD == 1 && warp >= EDGE_WARP0 && warp < EDGE_WARP0 + EDGE_WARPS) {
         // ======================= data gradient: column terms of the padding adjoint, fp32 on the CUDA cores =======================
-        // C[e][n] = sum_k dy[edge pixel][k] * wf[k][n]   (n = (ky, g, o); the tap that would have left the image comes back onto the edge pixel).
-        // Items (edge, n) are dealt round-robin to the 64 threads; an image row piece has one edge (W > 128) or two (W = 128).
-        constexpr int ITEMS = 2 * HALF, PER = (ITEMS + FS_EDGE_WARPS * 32 - 1) / (FS_EDGE_WARPS * 32);
-        const int et = tid - FS_EDGE_WARP0 * 32;
+        // C[e][n] = sum_k dy[edge pixel e][k] * wf[e][k][n]   (n = (ky, g, o); the tap that would have left the image comes back onto the edge pixel).
+        // A row piece has one edge (W > 128: 48 NG items) or two (W = 128: 96 NG items), dealt round-robin to the threads; the weights are resident in
+        // shared memory (with ~200 KB of it in use there is next to no L1 left: as __ldg they were L2 round trips).
+        constexpr int NT = (EDGE_WARPS > 0 ? EDGE_WARPS : 1) * 32, PER = (2 * HALF + NT - 1) / NT;
+        const int et = tid - EDGE_WARP0 * 32;
         float cacc[PER];
 #pragma unroll
         for (int i = 0; i < PER; ++i) cacc[i] = 0.f;
-        const float* wedge = a.wedge + (size_t)blockIdx.y * 2 * a.K * HALF;
         FsRing rr(RS), ra(AS);
         for (int step = 0; step < nsteps; ++step) {
             const bool img_l = (it.t == 0), img_r = (it.t == T - 1);
+            int nitems = 0, ebase = 0;   // item = e * HALF + n
+            if (!(a.ablate & 1)) {
+                if (img_l && img_r) nitems = 2 * HALF;
+                else if (img_l || img_r) { nitems = HALF; ebase = img_l ? 0 : HALF; }
+            }
             for (int c = 0; c < nchunks; ++c, rr.next(), ra.next()) {
                 const int rs = rr.idx, as = ra.idx;
+                if (et == 0 && c == 0) FS_STAMP(9, step);
                 if (ra.wrapped) mbar_wait(a_empty + as, ra.phase ^ 1);   // same gate as the other producers: never two arrivals in one phase
                 mbar_wait(raw_full + rs, rr.phase);
-                const float* raw = reinterpret_cast<const float*>(raw_s + (size_t)rs * L.raw_stage);
-                if (img_l || img_r) {
-#pragma unroll
-                    for (int i = 0; i < PER; ++i) {
-                        const int item = et + i * FS_EDGE_WARPS * 32;
-                        const int e = item / HALF, n = item - e * HALF;
-                        if (item < ITEMS && (e == 0 ? img_l : img_r)) {
-                            const float* dyp = raw + (e == 0 ? 4 : 3 + Wt);
-                            const float* we = wedge + ((size_t)e * a.K + c * KC) * HALF + n;
-                            float sacc = cacc[i];
-#pragma unroll
-                            for (int k = 0; k < KC; ++k) sacc = fmaf(dyp[k * rpx], __ldg(we + (size_t)k * HALF), sacc);
-                            cacc[i] = sacc;
-                        }
-                    }
-                    if (c == nchunks - 1) {
-                        float* eb = edge_s + (size_t)(step & (FS_ES - 1)) * 2 * HALF;
-#pragma unroll
-                        for (int i = 0; i < PER; ++i) {
-                            const int item = et + i * FS_EDGE_WARPS * 32;
-                            if (item < ITEMS) eb[item] = cacc[i];
-                            cacc[i] = 0.f;
-                        }
-                    }
-                }
+                const float* raw0 = reinterpret_cast<const float*>(raw_s + (size_t)rs * L.raw_stage);
+                fs_edge_chunk<KC, HALF, NT, PER>(cacc, et, nitems, ebase, raw0, wedge_s, a.K, c, rpx, Wt, c == nchunks - 1, edge_s + (size_t)(step & (FS_ES - 1)) * 2 * HALF);
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(raw_empty + rs); mbar_arrive(a_full + as); }   // the edge row is published before the MMAs of this step may start
+                if (et == 0 && c == nchunks - 1) FS_STAMP(15, step);
             }
             it.next();
         }
@@ -479,7 +515,8 @@ __global__ void __launch_bounds__(fs_threads(PAD), 1) conv3x3_fs_kernel(const Fs
                 auto emit = [&](int row, const float* v) {
                     float* op = orow + (size_t)(g * 16) * plane + (size_t)row * W;
                     float old[8];
-                    if (accum) {   // all eight loads first: one memory round trip instead of eight dependent ones
+                    if (a.ablate & 2) return;
+                    if (accum && !(a.ablate & 4)) {   // all eight loads first: one memory round trip instead of eight dependent ones
 #pragma unroll
                         for (int j = 0; j < 8; ++j) old[j] = __ldcg(op + (size_t)j * plane);
                     }
@@ -555,11 +592,11 @@ int launch_fs(const FsArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, i
     const FsLayout L = fs_layout(a.K / KC, NG, KC, PAD == 1);
     auto kern = conv3x3_fs_kernel<KIND, NG, PAD, AFFINE, STATS, false, MM>;
     if (a.trace) {
-        if constexpr (PAD == 0 && !AFFINE && !STATS && NG == 1 && MM == 128) kern = conv3x3_fs_kernel<KIND, NG, PAD, AFFINE, STATS, true, MM>;   // traced build: plain forward only
+        if constexpr (!AFFINE && !STATS && MM == 128 && KIND != 1) kern = conv3x3_fs_kernel<KIND, NG, PAD, AFFINE, STATS, true, MM>;   // traced build: plain forward and data gradient
     }
     SIFNN_REQUIRE(L.total <= 227 * 1024, "conv3x3_fs: shared-memory budget exceeded (K=%d)", a.K);
     SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    kern<<<dim3(gx, gy), fs_threads(PAD), L.total, st>>>(a, tm1, tm2);
+    kern<<<dim3(gx, gy), fs_threads(PAD, NG), L.total, st>>>(a, tm1, tm2);
     return sifnn::check_launch("conv3x3_fs_kernel");
 }
 
@@ -602,6 +639,7 @@ int run_fs(int pad, const float* in, const float* in2, int K1, const float* in_s
     a.nrows = B * H;
     a.K1 = in2 ? K1 : K;
     a.trace = g_fs_trace;
+    { const char* e = getenv("SIFNN_FS_ABLATE"); a.ablate = e ? atoi(e) : 0; }
     const int NG = fs_groups(K, O, kind);
     const int gy = O / (16 * NG);
     int gx = sifnn::num_sms() / gy;

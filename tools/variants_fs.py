@@ -25,6 +25,7 @@ for sh in (sys.argv[1:] or ["16x16x256", "32x16x256", "64x32x128"]):
         "stats": lambda: _lib.call("sifnn_conv3x3_fwd_fs", x.data_ptr(), None, None, w.data_ptr(), out.data_ptr(), stats.data_ptr(), wprep.data_ptr(), B, ci, co, hw, hw, st),
         "affine+stats": lambda: _lib.call("sifnn_conv3x3_fwd_fs", x.data_ptr(), sc.data_ptr(), shf.data_ptr(), w.data_ptr(), out.data_ptr(), stats.data_ptr(), wprep.data_ptr(), B, ci, co, hw, hw, st),
         "dgrad": lambda: _lib.call("sifnn_conv3x3_dgrad_fs", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), 0, wprep.data_ptr(), B, ci, co, hw, hw, st),
+        "dgrad+acc": lambda: _lib.call("sifnn_conv3x3_dgrad_fs", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, wprep.data_ptr(), B, ci, co, hw, hw, st),
     }
     row = []
     for name, fn in fns.items():
