@@ -176,10 +176,10 @@ def test_autograd_dropin_step_vs_golden(kind, tc_mode):
     assert rel_err(grads, g["grads"]) < TOL
     # per-tensor check as well.  Some tensors (conv weights feeding a BatchNorm) have gradients that are pure
     # cancellation residue, 1e-5 of the others: there the reference's own fp32 result is noise-limited, so the
-    # yardstick is the oracle in fp64 and the bar "within 1e-4 of the tensor's max, or no worse than 10x the
-    # reference's own fp32 error on that tensor" in strict-fp32 mode; 30x with the tensor-core kernels, whose
-    # fp32 accumulation truncates instead of rounding (tools/tc_accuracy_probe.py: 2-3e-6 per convolution).
-    mult = 50 if tc_mode else 10
+    # yardstick is the oracle in fp64 and the bar "within 1e-4 of the tensor's max, or no worse than 3x the
+    # reference's own fp32 error on that tensor" in both modes.  Measured in round 2 (profiles/r2_parity_measured.txt):
+    # worst tensor 3.1e-4 where the reference's fp32 is at 2.8e-4 -> ratio 1.1 (round 1 allowed 50x / 10x).
+    mult = 3
     ref64 = O.Trainer(load_ckpt("1009"), kind, alpha, gamma, lr, dtype=torch.float64)
     ref64.loss_and_grads(*syn_inputs())
     g64 = ref64.flat_grads()
@@ -244,8 +244,9 @@ def test_loss_curve_100_steps(tc_mode):
     """100 SR2 steps (B=4, lr 1e-3) from the seed-0 reference initialisation against the reference's own fp64
     curve (tests/golden/curve_100.npz).  fp32 training is chaotic: the reference's fp32 run itself drifts from its
     fp64 run (up to 3e-3 by step 87).  Bar per step: rel 1e-4 over the first 20 steps in strict-fp32
-    mode (2e-4 with the tensor-core kernels, whose accumulation truncates), then
-    max(2e-4, 10x the reference's own fp32-vs-fp64 drift so far) -- same order of magnitude as the reference's
+    mode (1.6e-4 with the tensor-core kernels, whose accumulation truncates; measured 7.9e-5 / 1.2e-4, the reference's
+    own fp32 run 5.0e-5: profiles/r2_parity_measured.txt), then
+    max(2e-4, 5x the reference's own fp32-vs-fp64 drift so far) -- same order of magnitude as the reference's
     own rounding noise; both series are printed and saved.  "So far" looks 3 steps ahead: the drift arrives in
     chaotic bursts (the reference's fp32 run jumps from 1e-5 to 2e-3 within steps 81..84) and which step a burst
     starts on is itself rounding noise."""
@@ -265,8 +266,8 @@ def test_loss_curve_100_steps(tc_mode):
     print("\nloss-curve rel.err vs reference fp64: ours max %.2e (first 20: %.2e, first 60: %.2e); reference fp32 max %.2e (first 20: %.2e, first 60: %.2e)"
           % (ours.max(), ours[:20].max(), ours[:60].max(), floor.max(), floor[:20].max(), floor[:60].max()))
     assert rec[-1, 2] < 0.6 * rec[0, 2]
-    assert ours[:20].max() < (2e-4 if tc_mode else 1e-4)
-    bound = np.maximum(2e-4, 10 * np.maximum.accumulate(np.concatenate([floor[3:], np.repeat(floor[-1], 3)])))
+    assert ours[:20].max() < (1.6e-4 if tc_mode else 1e-4)
+    bound = np.maximum(2e-4, 5 * np.maximum.accumulate(np.concatenate([floor[3:], np.repeat(floor[-1], 3)])))
     assert (ours <= bound).all(), np.nonzero(ours > bound)
 
 
