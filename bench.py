@@ -30,10 +30,11 @@ import torch  # noqa: E402
 PATCH_MPIX = 256 * 256 / 1e6
 FWD_GFLOP, STEP_GFLOP = 3.605, 10.78  # per patch, SURVEY section 8d
 # ncu --set full summaries (profiles/) of one launch of each kernel class, used for roofline.traffic
-NCU_SUMMARIES = {"conv3x3_fs_kernel fwd": "r2l_ncu_full_conv3x3_fs_fwd_16x16x256_summary.csv",
-                 "conv3x3_fs_kernel dgrad": "r2l_ncu_full_conv3x3_fs_fwd_16x16x256_summary.csv",
+NCU_SUMMARIES = {"wgrad_km_kernel": "r2_ncu_full_wgrad_km_32x16x256_summary.csv",
+                 "conv3x3_fs_kernel fwd": "r2_ncu_full_conv3x3_fs_fwd_32x16x256_summary.csv",
+                 "conv3x3_fs_kernel dgrad": "r2_ncu_full_conv3x3_fs_dgrad_32x16x256_summary.csv",
                  "conv3x3_ff_kernel fwd": "r2j_ncu_full_conv3x3_ff_16x16x256_summary.csv",
-                 "conv3x3_ff_kernel dgrad": "r2j_ncu_full_conv3x3_ff_16x16x256_summary.csv",
+                 "conv3x3_ff_kernel dgrad": "r2_ncu_full_conv3x3_ff_dgrad_128x64x64_summary.csv",
                  "wgrad_tc_kernel": "r1l_ncu_full_wgrad_tc_32x16x256_summary.csv",
                  "wgrad_kernel": "r1i_ncu_full_wgrad_16x16x256_summary.csv",
                  "conv3x3_tc_kernel fwd": "r1j_ncu_full_conv3x3_tc_64x32x128_summary.csv",

@@ -13,14 +13,20 @@
 //                      the edge elements (copy kx=0 [x = 0] += dy[0], copy kx=2 [x = W-1] += dy[W-1]); N = 6 * C_out
 //   D[(r, s, c)][(kx, s', o)] += X . dy          one MMA per 16 pixels computes all nine taps and all four hi/lo products
 //
-// Operand formats: X (activations, O(1) magnitudes) FP16 hi + lo = 22 significant bits; dy (gradients, tiny magnitudes) BF16 hi + lo = 16 bits
-// with the full fp32 exponent range; kind::f16 takes the two formats independently.  Accumulators stay in TMEM for the whole kernel, rotating over
+// Operand formats: both BF16 hi + lo (16 significant bits, full fp32 exponent range: gradients are tiny).  FP16 for the activations would give 22 bits,
+// but kind::f16 rejects mixed FP16 x BF16 operands on sm_100a (illegal instruction, tools/km_fmt_probe.py) and FP16 gradients would need a scale.  Accumulators stay in TMEM for the whole kernel, rotating over
 // NSETS independent sets (the tensor core's fp32 accumulation truncates: shorter chains, and two MMA issuers can alternate tiles without ever
 // sharing a set); one drain at the end writes a per-CTA partial that a fixed-order reduction sums (deterministic).
 // More than 32 channels on either side are split over blockIdx.y into 32-channel blocks.
 //
 // Warp roles (11 warps): 0 TMA loader, 1 and 2 MMA issuers (even / odd tiles), 3..10 transformers (raw fp32 -> BatchNorm affine + ReLU -> hi / lo
 // split -> operand tiles), which also drain the accumulators at the end.
+//
+// What bounds it (profiles/r2_ncu_full_wgrad_km_16x16x256_summary.csv, r2w/r2za_profile_wgrad.log): shared-memory bandwidth.  Per 8 x 32 tile the
+// transformers read 45 KB of raw fp32 and write 69 KB of operands, the MMAs read another ~80 KB; ncu shows the shared-memory data pipe 37 % (tensor
+// core reads) + 45 % (LSU) busy, DRAM traffic = algorithmic bytes, tensor pipe 32 %.  Tried and measured: pairing two dy rows per MMA (N = 192, half
+// the MMAs: kept, no time change), 16 instead of 8 transformer warps (no change), 4-row tiles with four raw stages (slower: 84 -> 107 us), a raw
+// ring of up to four stages where it fits (32 -> 16: 137 -> 131 us, 32 x 32 blocks: 131 -> 118 us; kept).
 #include "tc_common.cuh"
 
 #include <cstdlib>
@@ -39,7 +45,7 @@ constexpr int KM_THREADS = (KM_XF_WARP0 + KM_XF_WARPS) * 32;
 struct KmArgs {
     const float* in_scale;
     const float* in_shift;
-    float* partial;          // [gridDim.x][O][K][9]
+    float* partial;          // [gridDim.x * PAIR][O][K][9]
     int B, K, O, H, W;
     int tiles_x, tiles_y, num_tiles;
     int nco;                 // 32-channel (or 16-channel) blocks of the output channels: blockIdx.y = ci_block * nco + co_block
@@ -53,10 +59,15 @@ struct KmCfg {
     static constexpr int DR = R * 6 * CO;                  // dy rows per octet plane: (row, kx, hi / lo, channel)
     static constexpr int X_TILE = G8 * XR * 16, D_TILE = G8 * DR * 16, STAGE = X_TILE + D_TILE;
     static constexpr int RAW_X = TR * CI * KM_XW * 4, RAW_D = R * CO * KM_DW * 4, RAW_STAGE = RAW_X + RAW_D;
-    static constexpr int N = 6 * CO;
-    static constexpr int NSETS = (512 / N) >= 4 ? 4 : 2;
+    static constexpr int PAIR = (CO == 16) ? 2 : 1;        // dy rows per MMA: an MMA costs ~111 clocks up to N = 144 and ~130 at N = 192, so two 16-channel
+                                                           // dy rows share one instruction (and one M = 128 window of FOUR input rows)
+    static constexpr int N = PAIR * 6 * CO;                // 192
+    static constexpr int NSETS = 2;
     static constexpr int MB = CI / 16;                     // MMAs per K step
-    static constexpr size_t BYTES = 1024 + 2 * (size_t)STAGE + 2 * (size_t)RAW_STAGE;
+    static constexpr int RS_FIT = (227 * 1024 - 1024 - 2 * STAGE) / RAW_STAGE;
+    static constexpr int RS = RS_FIT >= 4 ? 4 : RS_FIT;    // raw (TMA) stages: the loads of the next tiles are in flight while this one is converted
+    static constexpr size_t BYTES = 1024 + 2 * (size_t)STAGE + RS * (size_t)RAW_STAGE;
+    static_assert(RS >= 2, "at least two raw stages");
     static_assert(CI == 16 || CI == 32, "16 or 32 input channels per CTA");
     static_assert(N <= 256 && NSETS * N <= 512, "accumulator sets must fit TMEM");
     static_assert(RAW_X % 128 == 0 && RAW_D % 128 == 0 && STAGE % 128 == 0 && X_TILE % 128 == 0, "TMA destinations / tiles stay 128-byte aligned");
@@ -94,15 +105,15 @@ __device__ __forceinline__ void km_split8(const float* v, int fmt, uint4& hi, ui
 template <int CI, int CO, int R, bool AFFINE>
 __global__ void __launch_bounds__(KM_THREADS, 1) wgrad_km_kernel(const KmArgs a, const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy) {
     using C = KmCfg<CI, CO, R>;
-    constexpr int TR = C::TR, G8 = C::G8, XR = C::XR, DR = C::DR, N = C::N, NSETS = C::NSETS, MB = C::MB;
+    constexpr int TR = C::TR, G8 = C::G8, XR = C::XR, DR = C::DR, N = C::N, NSETS = C::NSETS, MB = C::MB, RS = C::RS;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     uint64_t* ab_full = bars;           // [2]
     uint64_t* ab_empty = bars + 2;      // [2]
-    uint64_t* raw_full = bars + 4;      // [2]
-    uint64_t* raw_empty = bars + 6;     // [2]
-    uint64_t* acc_full = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* raw_full = bars + 4;      // [RS <= 4]
+    uint64_t* raw_empty = bars + 8;     // [RS <= 4]
+    uint64_t* acc_full = bars + 12;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     float* sc_s = reinterpret_cast<float*>(smem + 128);    // [CI]
     float* sh_s = sc_s + 32;
     unsigned char* stage0 = smem + 1024;
@@ -114,10 +125,8 @@ __global__ void __launch_bounds__(KM_THREADS, 1) wgrad_km_kernel(const KmArgs a,
     const int tiles_per_img = a.tiles_x * a.tiles_y;
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(ab_full + s, KM_XF_WARPS); mbar_init(ab_empty + s, 1);
-            mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, KM_XF_WARPS);
-        }
+        for (int s = 0; s < 2; ++s) { mbar_init(ab_full + s, KM_XF_WARPS); mbar_init(ab_empty + s, 1); }
+        for (int s = 0; s < RS; ++s) { mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, KM_XF_WARPS); }
         mbar_init(acc_full, 2);
         fence_mbar_init();
     }
@@ -142,8 +151,8 @@ __global__ void __launch_bounds__(KM_THREADS, 1) wgrad_km_kernel(const KmArgs a,
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++g) {
             int b, y0, x0;
             tile_coords(tile, b, y0, x0);
-            const int rs = g & 1;
-            if (g >= 2) mbar_wait(raw_empty + rs, ((g >> 1) - 1) & 1);
+            const int rs = g % RS;
+            if (g >= RS) mbar_wait(raw_empty + rs, ((g / RS) - 1) & 1);
             if (lane == 0) {
                 unsigned char* dst = raw0 + (size_t)rs * C::RAW_STAGE;
                 mbar_arrive_expect_tx(raw_full + rs, C::RAW_STAGE);
@@ -167,13 +176,13 @@ __global__ void __launch_bounds__(KM_THREADS, 1) wgrad_km_kernel(const KmArgs a,
                 const uint32_t d = tmem_base + (uint32_t)((g % NSETS) * N);
                 const bool first_use = g < NSETS;
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
+                for (int r = 0; r < R; r += C::PAIR) {
 #pragma unroll
                     for (int j = 0; j < KM_WT / 16; ++j) {
                         const uint64_t db = make_desc(dt + (uint32_t)((2 * j * DR + r * 6 * CO) * 16), DR * 16, 128);
 #pragma unroll
                         for (int mb = 0; mb < MB; ++mb) {
-                            // CI = 16: rows (r, s, c), window = 3 tile rows x 32;  CI = 32: rows (s, r, c), hi window then lo window
+                            // CI = 16: rows (r, s, c), window = 3 (4 with paired dy rows) tile rows x 32;  CI = 32: rows (s, r, c), hi window then lo window
                             const int row0 = (CI == 16) ? r * 32 : (mb * TR + r) * 32;
                             const uint64_t da = make_desc(xt + (uint32_t)((2 * j * XR + row0) * 16), XR * 16, 128);
                             umma_bf16(d, da, db, idesc, (first_use && r == 0 && j == 0 && mb == 0) ? 0u : 1u);
@@ -196,10 +205,11 @@ __global__ void __launch_bounds__(KM_THREADS, 1) wgrad_km_kernel(const KmArgs a,
             const int s = g & 1;
             unsigned char* xtile = stage0 + (size_t)s * C::STAGE;
             unsigned char* dtile = xtile + C::X_TILE;
-            const float* rawx = reinterpret_cast<const float*>(raw0 + (size_t)s * C::RAW_STAGE);
-            const float* rawd = reinterpret_cast<const float*>(raw0 + (size_t)s * C::RAW_STAGE + C::RAW_X);
+            const int rs = g % RS;
+            const float* rawx = reinterpret_cast<const float*>(raw0 + (size_t)rs * C::RAW_STAGE);
+            const float* rawd = reinterpret_cast<const float*>(raw0 + (size_t)rs * C::RAW_STAGE + C::RAW_X);
             if (g >= 2) mbar_wait(ab_empty + s, ((g >> 1) - 1) & 1);
-            mbar_wait(raw_full + s, (g >> 1) & 1);
+            mbar_wait(raw_full + rs, (g / RS) & 1);
             // ---- input: rows clamped onto the image (replicate padding along y); BatchNorm affine + ReLU; hi / lo
 #pragma unroll 2
             for (int item = xt; item < XI; item += KM_XF_THREADS) {
@@ -248,19 +258,24 @@ __global__ void __launch_bounds__(KM_THREADS, 1) wgrad_km_kernel(const KmArgs a,
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(raw_empty + s); mbar_arrive(ab_full + s); }
+            if (lane == 0) { mbar_arrive(raw_empty + rs); mbar_arrive(ab_full + s); }
         }
 
         // ======================= drain: TMEM -> sum over sets and over the hi / lo blocks -> per-CTA partial =======================
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        const int quad = warp & 3;                         // TMEM lane quadrant of this warp = tile row of the window = ky
-        const int half = ((warp - KM_XF_WARP0) >> 2) & 1;  // the two warps of a quadrant split the (kx, 8-channel block) list
+        const int quad = warp & 3;                         // TMEM lane quadrant of this warp = input row of the window
+        const int half = (warp - KM_XF_WARP0) >> 2;        // the warps of a quadrant split the (kx, 8-channel block) list
         const int my_tiles = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int sets_used = my_tiles < NSETS ? my_tiles : NSETS;
-        constexpr int NBLK = 3 * (CO / 8);
-        if (quad < 3) {
-            for (int blk = half; blk < NBLK; blk += 2) {
+        constexpr int NBLK = 3 * (CO / 8), PAIR = C::PAIR;
+        // window row q pairs with dy row p of the MMA as tap ky = q - p; with paired dy rows a tap gets its two halves from two quadrants, which go
+        // to two partial slots (2 blockIdx.x + p) that the fixed-order reduction adds
+#pragma unroll
+        for (int pr = 0; pr < PAIR; ++pr) {
+            const int ky = quad - pr;
+            if (ky < 0 || ky > 2) continue;
+            for (int blk = half; blk < NBLK; blk += KM_XF_WARPS / 4) {
                 const int kx = blk / (CO / 8), ob = blk - kx * (CO / 8);
                 float acc[8];
 #pragma unroll
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(KM_THREADS, 1) wgrad_km_kernel(const KmArgs a,
                 for (int set = 0; set < NSETS; ++set) {
                     if (set >= sets_used) break;
                     float d1[8], d2[8];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + set * N + (kx * 2) * CO + ob * 8;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + set * N + pr * 6 * CO + (kx * 2) * CO + ob * 8;
                     tmem_ld8(taddr, d1);
                     tmem_ld8(taddr + CO, d2);
                     tmem_ld_wait();
@@ -284,7 +299,7 @@ __global__ void __launch_bounds__(KM_THREADS, 1) wgrad_km_kernel(const KmArgs a,
                     const int c = (CI == 16) ? (lane & 15) : lane;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        a.partial[(((size_t)blockIdx.x * a.O + co0 + ob * 8 + j) * a.K + ci0 + c) * 9 + quad * 3 + kx] = acc[j];
+                        a.partial[((((size_t)blockIdx.x * PAIR + pr) * a.O + co0 + ob * 8 + j) * a.K + ci0 + c) * 9 + ky * 3 + kx] = acc[j];
                 }
             }
         }
@@ -339,7 +354,12 @@ int launch_km(const float* in, const float* dy, KmArgs a, int S, bool affine, cu
 
 int km_ci(int Cin) { return Cin == 16 ? 16 : 32; }
 int km_co(int Cout) { return Cout == 16 ? 16 : 32; }
-int km_rows(int Cin, int Cout) { return (km_ci(Cin) == 16 && km_co(Cout) == 16) ? 8 : ((km_ci(Cin) == 32 && km_co(Cout) == 32) ? 2 : 4); }
+int km_rows16() {   // rows per tile of the 16 -> 16 configuration: 8 (two raw stages fit) or 4 (four raw stages); SIFNN_KM_R16 for A/B runs
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SIFNN_KM_R16"); v = (e && atoi(e) == 4) ? 4 : 8; }
+    return v;
+}
+int km_rows(int Cin, int Cout) { return (km_ci(Cin) == 16 && km_co(Cout) == 16) ? km_rows16() : ((km_ci(Cin) == 32 && km_co(Cout) == 32) ? 2 : 4); }
 bool km_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SIFNN_WGRAD_KM"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -358,7 +378,7 @@ extern "C" int sifnn_conv3x3_wgrad_km_supported(int Cin, int Cout, int H, int W)
 
 extern "C" size_t sifnn_conv3x3_wgrad_km_workspace(int B, int Cin, int Cout, int H, int W) {
     if (B <= 0 || !sifnn_conv3x3_wgrad_km_supported(Cin, Cout, H, W)) return 0;
-    return (size_t)sifnn::num_sms() * Cout * Cin * 9 * sizeof(float);
+    return (size_t)2 * sifnn::num_sms() * Cout * Cin * 9 * sizeof(float);   // two partial slots per CTA when dy rows are paired (16 output channels per CTA)
 }
 
 extern "C" int sifnn_conv3x3_wgrad_km(const float* in, const float* in_scale, const float* in_shift, const float* dy, float* dw, void* workspace,
@@ -381,12 +401,12 @@ extern "C" int sifnn_conv3x3_wgrad_km(const float* in, const float* in_scale, co
     const int ntiles = B * (W / KM_WT) * (H / km_rows(Cin, Cout));
     if (S > ntiles) S = ntiles;
     int rc;
-    if (ci == 16 && co == 16) rc = launch_km<16, 16, 8>(in, dy, a, S, affine, st);
+    if (ci == 16 && co == 16) rc = km_rows16() == 8 ? launch_km<16, 16, 8>(in, dy, a, S, affine, st) : launch_km<16, 16, 4>(in, dy, a, S, affine, st);
     else if (ci == 32 && co == 16) rc = launch_km<32, 16, 4>(in, dy, a, S, affine, st);
     else if (ci == 16 && co == 32) rc = launch_km<16, 32, 4>(in, dy, a, S, affine, st);
     else rc = launch_km<32, 32, 2>(in, dy, a, S, affine, st);
     SIFNN_TRY(rc);
     const int n = Cout * Cin * 9;
-    wgrad_km_reduce_kernel<<<(n + 31) / 32, 1024, 0, st>>>(a.partial, dw, n, S);
+    wgrad_km_reduce_kernel<<<(n + 31) / 32, 1024, 0, st>>>(a.partial, dw, n, co == 16 ? 2 * S : S);
     return sifnn::check_launch("wgrad_km_reduce_kernel");
 }
