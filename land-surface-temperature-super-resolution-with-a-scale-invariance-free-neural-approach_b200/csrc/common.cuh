@@ -25,11 +25,55 @@ int conv3x3_fwd_tc_prepped(const float* in, const float* in_scale, const float* 
 int conv3x3_dgrad_tc_main_prepped(const float* dy, const void* wprep, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
 int conv3x3_dgrad_border_cols(const float* dy, const float* w, float* dx, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
 
+// BatchNorm finalize (bn_train_finalize_kernel, model.py:136 nn.BatchNorm2d in training mode) folded into the producing convolution: every CTA takes a
+// ticket after its statistics atomics; the CTA that draws the last one turns the sums into scale / shift / mean / invstd and updates the running
+// buffers -- one launch fewer per BatchNorm layer on the critical path of the step.  `counter` must be zero at launch; the last CTA re-arms it.
+struct BnTail {
+    unsigned int* counter;   // nullptr = no tail (the caller finalizes with sifnn_bn_train_finalize)
+    const float* gamma;
+    const float* beta;
+    float* running_mean;     // may be nullptr (with running_var)
+    float* running_var;
+    float* scale;
+    float* shift;
+    float* save_mean;
+    float* save_invstd;
+    double n;                // elements per channel: B * H * W
+};
+#ifdef __CUDACC__
+// Call from ALL threads of the CTA after a __syncthreads() that follows the CTA's statistics atomics, each issuing thread having executed
+// __threadfence() after its atomics.  `flag` is a shared-memory int.
+__device__ __forceinline__ void bn_tail_finalize(const BnTail& t, const double* stats, int C, unsigned int total_ctas, int* flag) {
+    if (threadIdx.x == 0) *flag = (atomicAdd(t.counter, 1u) == total_ctas - 1u) ? 1 : 0;
+    __syncthreads();
+    if (*flag) {
+        __threadfence();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const double mean = __ldcg(stats + c) / t.n;
+            double var = __ldcg(stats + C + c) / t.n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float invstd = (float)(1.0 / sqrt(var + 1e-5));
+            const float sc = t.gamma[c] * invstd;
+            t.scale[c] = sc;
+            t.shift[c] = fmaf(-(float)mean, sc, t.beta[c]);
+            t.save_mean[c] = (float)mean;
+            t.save_invstd[c] = invstd;
+            if (t.running_mean) {
+                const double unbiased = t.n > 1.0 ? var * t.n / (t.n - 1.0) : var;
+                t.running_mean[c] = (float)(0.9 * (double)t.running_mean[c] + 0.1 * mean);
+                t.running_var[c] = (float)(0.9 * (double)t.running_var[c] + 0.1 * unbiased);
+            }
+        }
+        if (threadIdx.x == 0) *t.counter = 0u;
+    }
+}
+#endif
+
 // Full-fold tensor-core convolution (csrc/conv3x3_ff.cu): all nine taps in the MMA's N dimension, shift-and-add epilogue, padding adjoint included.
 bool conv3x3_ff_supported(int K, int O, int H, int W);
 int ff_prep(const float* const* w, void* const* wprep, const int* K, const int* O, const int* w_so, const int* w_sk, const int* flip, int n, cudaStream_t st);
 int conv3x3_fwd_ff_prepped(const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, float* out, double* stats,
-                           int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
+                           int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st, const BnTail* tail = nullptr);
 int conv3x3_dgrad_ff_prepped(const float* dy, const void* wprep, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
 
 // Fold + shift tensor-core convolution for widths that are multiples of 128 (csrc/conv3x3_fs.cu): ky in the MMA's N dimension, kx through shifted
@@ -39,7 +83,7 @@ size_t conv3x3_fs_wedge_bytes(int K, int O);
 int fs_prep(const float* const* w, void* const* wprep, float* const* wedge, const int* K, const int* O, const int* w_so, const int* w_sk, const int* flip, int n,
             cudaStream_t st);
 int conv3x3_fwd_fs_prepped(const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, float* out, double* stats,
-                           int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
+                           int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st, const BnTail* tail = nullptr);
 int conv3x3_dgrad_fs_prepped(const float* dy, const void* wprep, const float* wedge, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
 
 // "do once per device" (cudaFuncSetAttribute is per device; a process may drive several GPUs, possibly from several threads)

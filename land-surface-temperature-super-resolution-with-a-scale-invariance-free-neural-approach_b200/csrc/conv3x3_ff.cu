@@ -46,6 +46,7 @@ constexpr int FF_A_TILE = 2 * 128 * 16;    // bytes of one (hi or lo) activation
 #define FF_STAMP(ev, idx) do { if (DBG && a.trace && blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 256) a.trace[(ev) * 256 + (idx)] = clock64(); } while (0)
 
 struct FfArgs {
+    sifnn::BnTail tail;   // optional fused BatchNorm finalize (forward with statistics)
     const float* in_scale;
     const float* in_shift;
     const unsigned char* wprep;   // [O / 16][chunk][hi, lo][2 q][144][16 B]
@@ -526,6 +527,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs 
                 const double v = (double)part[(0 * 2 + stat) * 16 * NG + ch] + (double)part[(1 * 2 + stat) * 16 * NG + ch] + (double)part[(2 * 2 + stat) * 16 * NG + ch] +
                                  (double)part[(3 * 2 + stat) * 16 * NG + ch];
                 atomicAdd(a.stats + (size_t)stat * a.O + blockIdx.y * NG * 16 + ch, v);
+                __threadfence();   // ordered before this CTA's ticket of the BatchNorm tail
             }
         }
     }
@@ -534,6 +536,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs 
     if (warp == FF_MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
+    }
+    if constexpr (STATS) {
+        if (a.stats && a.tail.counter) {
+            __shared__ int tail_flag;
+            sifnn::bn_tail_finalize(a.tail, a.stats, a.O, gridDim.x * gridDim.y, &tail_flag);
+        }
     }
 }
 
@@ -579,7 +587,7 @@ bool ff_shape_ok(int K, int O, int H, int W) {
 }
 
 // in2 != nullptr: channels [K1, K) come from a second tensor (the two halves of a channel concat read in place)
-int run_ff(int pad, const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, float* out, double* stats,
+int run_ff(const sifnn::BnTail* tail, int pad, const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, float* out, double* stats,
            int accumulate, int B, int K, int O, int H, int W, cudaStream_t st) {
     SIFNN_REQUIRE(ff_shape_ok(K, O, H, W), "conv3x3_ff: unsupported shape K=%d O=%d H=%d W=%d", K, O, H, W);
     const int kind = sifnn::tc_split_kind(pad);
@@ -588,6 +596,7 @@ int run_ff(int pad, const float* in, const float* in2, int K1, const float* in_s
     SIFNN_REQUIRE(!in2 || (K1 % KC == 0 && K1 > 0 && K1 < K), "conv3x3_ff: the split point of a two-source input must be a multiple of %d", KC);
     FfArgs a{};
     a.in_scale = in_scale; a.in_shift = in_shift; a.wprep = static_cast<const unsigned char*>(wprep); a.out = out; a.stats = stats;
+    if (tail && stats) a.tail = *tail;
     a.B = B; a.K = K; a.O = O; a.H = H; a.W = W; a.accumulate = accumulate ? 1 : 0;
     a.G = W < 128 ? 128 / W : 1;
     a.nrows = B * H;
@@ -669,11 +678,11 @@ int ff_prep(const float* const* w, void* const* wprep, const int* K, const int* 
 }
 
 int conv3x3_fwd_ff_prepped(const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, float* out, double* stats,
-                           int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st) {
-    return run_ff(0, in, in2, K1, in_scale, in_shift, wprep, out, stats, accumulate, B, Cin, Cout, H, W, st);
+                           int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st, const BnTail* tail) {
+    return run_ff(tail, 0, in, in2, K1, in_scale, in_shift, wprep, out, stats, accumulate, B, Cin, Cout, H, W, st);
 }
 int conv3x3_dgrad_ff_prepped(const float* dy, const void* wprep, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st) {
-    return run_ff(1, dy, nullptr, 0, nullptr, nullptr, wprep, dx, nullptr, accumulate, B, Cout, Cin, H, W, st);
+    return run_ff(nullptr, 1, dy, nullptr, 0, nullptr, nullptr, wprep, dx, nullptr, accumulate, B, Cout, Cin, H, W, st);
 }
 
 }  // namespace sifnn

@@ -74,6 +74,7 @@ constexpr int FS_ES = 16;                  // ring of edge-correction rows (the 
 #define FS_STAMP(ev, idx) do { if (DBG && a.trace && blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 256) a.trace[(ev) * 256 + (idx)] = clock64(); } while (0)
 
 struct FsArgs {
+    sifnn::BnTail tail;   // optional fused BatchNorm finalize (forward with statistics)
     int ablate;   // timing experiments only (SIFNN_FS_ABLATE): 1 skip the edge-column math, 2 skip the global stores, 4 skip the accumulate loads
     const float* in_scale;
     const float* in_shift;
@@ -559,6 +560,7 @@ __global__ void __launch_bounds__(fs_threads(PAD, NG), 1) conv3x3_fs_kernel(cons
                 const double v = (double)part[(0 * 2 + stat) * 16 * NG + ch] + (double)part[(1 * 2 + stat) * 16 * NG + ch] + (double)part[(2 * 2 + stat) * 16 * NG + ch] +
                                  (double)part[(3 * 2 + stat) * 16 * NG + ch];
                 atomicAdd(a.stats + (size_t)stat * a.O + blockIdx.y * NG * 16 + ch, v);
+                __threadfence();   // ordered before this CTA's ticket of the BatchNorm tail
             }
         }
     }
@@ -567,6 +569,12 @@ __global__ void __launch_bounds__(fs_threads(PAD, NG), 1) conv3x3_fs_kernel(cons
     if (warp == FS_MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
+    }
+    if constexpr (STATS) {
+        if (a.stats && a.tail.counter) {
+            __shared__ int tail_flag;
+            sifnn::bn_tail_finalize(a.tail, a.stats, a.O, gridDim.x * gridDim.y, &tail_flag);
+        }
     }
 }
 
@@ -626,7 +634,7 @@ int fs_groups(int K, int O, int kind) {   // output groups of 16 channels per CT
     return 2;
 }
 
-int run_fs(int pad, const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, const float* wedge, float* out,
+int run_fs(const sifnn::BnTail* tail, int pad, const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, const float* wedge, float* out,
            double* stats, int accumulate, int B, int K, int O, int H, int W, cudaStream_t st) {
     SIFNN_REQUIRE(fs_shape_ok(K, O, H, W), "conv3x3_fs: unsupported shape K=%d O=%d H=%d W=%d", K, O, H, W);
     const int kind = sifnn::tc_split_kind(pad);
@@ -639,6 +647,7 @@ int run_fs(int pad, const float* in, const float* in2, int K1, const float* in_s
     a.nrows = B * H;
     a.K1 = in2 ? K1 : K;
     a.trace = g_fs_trace;
+    if (tail && stats) a.tail = *tail;
     { const char* e = getenv("SIFNN_FS_ABLATE"); a.ablate = e ? atoi(e) : 0; }
     const int NG = fs_groups(K, O, kind);
     const int gy = O / (16 * NG);
@@ -736,11 +745,11 @@ int fs_prep(const float* const* w, void* const* wprep, float* const* wedge, cons
 }
 
 int conv3x3_fwd_fs_prepped(const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, float* out, double* stats,
-                           int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st) {
-    return run_fs(0, in, in2, K1, in_scale, in_shift, wprep, nullptr, out, stats, accumulate, B, Cin, Cout, H, W, st);
+                           int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st, const BnTail* tail) {
+    return run_fs(tail, 0, in, in2, K1, in_scale, in_shift, wprep, nullptr, out, stats, accumulate, B, Cin, Cout, H, W, st);
 }
 int conv3x3_dgrad_fs_prepped(const float* dy, const void* wprep, const float* wedge, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st) {
-    return run_fs(1, dy, nullptr, 0, nullptr, nullptr, wprep, wedge, dx, nullptr, accumulate, B, Cout, Cin, H, W, st);
+    return run_fs(nullptr, 1, dy, nullptr, 0, nullptr, nullptr, wprep, wedge, dx, nullptr, accumulate, B, Cout, Cin, H, W, st);
 }
 
 }  // namespace sifnn

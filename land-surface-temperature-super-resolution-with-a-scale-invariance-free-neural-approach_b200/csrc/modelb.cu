@@ -100,7 +100,8 @@ struct Workspace {
     float* R[3];
     float* U[3];
     float *scale, *shift, *mean, *invstd;  // bn_total each
-    double* stats;                          // 2 * bn_total (layer i at 2*bn_off[i])
+    double* stats;                          // 2 * bn_total (layer i at 2*bn_off[i]); the 32 tickets of the fused finalize follow directly (one memset)
+    unsigned int* bn_tickets;               // [SIFNN_MODELB_NBN] (rounded up to 32)
     double* bsums;                          // 2 * bn_total
     // training only
     float* g[SIFNN_MODELB_NBN];
@@ -130,6 +131,7 @@ Workspace carve(const Net& n, void* base, int B, int H, int W, int train) {
     w.mean = c.take<float>(n.bn_total);
     w.invstd = c.take<float>(n.bn_total);
     w.stats = c.take<double>(2 * n.bn_total);
+    w.bn_tickets = c.take<unsigned int>(32);
     w.bsums = c.take<double>(2 * n.bn_total);
     for (int i = 0; i < SIFNN_MODELB_NCONV; ++i)
         w.wprep_f[i] = c.take<char>(sifnn_conv3x3_tc_wprep_bytes((n.conv[i].cin + 7) / 8 * 8, n.conv[i].cout));
@@ -217,7 +219,7 @@ extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* pa
     cudaStream_t st = sifnn::as_stream(stream);
     const int hs[4] = {H, H / 2, H / 4, H / 8}, ws[4] = {W, W / 2, W / 4, W / 8};
     if (train) {
-        SIFNN_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(double) * 2 * n.bn_total, st));
+        SIFNN_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)(reinterpret_cast<char*>(w.bn_tickets + 32) - reinterpret_cast<char*>(w.stats)), st));   // sums + tickets
     } else {
         EvalTable t{};
         for (int i = 0; i < SIFNN_MODELB_NBN; ++i) { t.gamma_off[i] = n.gamma_off[i]; t.beta_off[i] = n.beta_off[i]; t.bn_off[i] = n.bn_off[i]; }
@@ -259,12 +261,22 @@ extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* pa
         const float* isc = aff >= 0 ? w.scale + n.bn_off[aff] : nullptr;
         const float* ish = aff >= 0 ? w.shift + n.bn_off[aff] : nullptr;
         double* st_ptr = (bn && train) ? w.stats + 2 * n.bn_off[i] : nullptr;
+        // BatchNorm finalize: inside the convolution (last CTA) for the fs / ff kernels, a separate launch otherwise
+        sifnn::BnTail tail{};
+        bool fused_tail = false;
+        if (bn && train) {
+            const int64_t o = n.bn_off[i];
+            tail = sifnn::BnTail{w.bn_tickets + i, params + n.gamma_off[i], params + n.beta_off[i], running_mean + o, running_var + o, w.scale + o, w.shift + o,
+                                 w.mean + o, w.invstd + o, (double)B * hs[l] * ws[l]};
+        }
         switch (fwd_kind(i)) {
             case KIND_FS:
-                SIFNN_TRY(sifnn::conv3x3_fwd_fs_prepped(in, nullptr, 0, isc, ish, w.wprep_f[i], out, st_ptr, 0, B, c.cin, c.cout, hs[l], ws[l], st));
+                SIFNN_TRY(sifnn::conv3x3_fwd_fs_prepped(in, nullptr, 0, isc, ish, w.wprep_f[i], out, st_ptr, 0, B, c.cin, c.cout, hs[l], ws[l], st, st_ptr ? &tail : nullptr));
+                fused_tail = st_ptr != nullptr;
                 break;
             case KIND_FF:
-                SIFNN_TRY(sifnn::conv3x3_fwd_ff_prepped(in, nullptr, 0, isc, ish, w.wprep_f[i], out, st_ptr, 0, B, c.cin, c.cout, hs[l], ws[l], st));
+                SIFNN_TRY(sifnn::conv3x3_fwd_ff_prepped(in, nullptr, 0, isc, ish, w.wprep_f[i], out, st_ptr, 0, B, c.cin, c.cout, hs[l], ws[l], st, st_ptr ? &tail : nullptr));
+                fused_tail = st_ptr != nullptr;
                 break;
             case KIND_TC:
                 SIFNN_TRY(sifnn::conv3x3_fwd_tc_prepped(in, isc, ish, w.wprep_f[i], bn ? nullptr : params + n.bias_off, out, st_ptr, B, c.cin, c.cout, hs[l],
@@ -274,7 +286,7 @@ extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* pa
                 SIFNN_TRY(sifnn_conv3x3_fwd(in, isc, ish, params + n.w_off[i], bn ? nullptr : params + n.bias_off, out, st_ptr, B, c.cin, c.cout, hs[l],
                                             ws[l], stream));
         }
-        if (bn && train) {
+        if (bn && train && !fused_tail) {
             const int64_t o = n.bn_off[i];
             SIFNN_TRY(sifnn_bn_train_finalize(w.stats + 2 * o, params + n.gamma_off[i], params + n.beta_off[i], running_mean + o, running_var + o,
                                               w.scale + o, w.shift + o, w.mean + o, w.invstd + o, c.cout, (double)B * hs[l] * ws[l], stream));
