@@ -447,14 +447,11 @@ def run_ours(args):
             l, n = tiles_d[i % 2]
             return sifnn_b200.super_resolve_tile(m, l, n, stats, batch=B, rank=rank, world_size=world, out=out_d)
 
-        def step_host(i):
+        def step_host(i):   # each rank moves only the rows its windows touch (super_resolve_tile_host)
             l, n = tiles_h[i % 2]
-            o = sifnn_b200.super_resolve_tile(m, l.to(dev, non_blocking=True), n.to(dev, non_blocking=True), stats, batch=B, rank=rank,
-                                              world_size=world, out=out_d)
-            out_h.copy_(o, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return out_h
-        h2d, d2h = (1200 * 1200 + 4800 * 4800) * 4, 4800 * 4800 * 4
+            return sifnn_b200.super_resolve_tile_host(m, l, n, stats, batch=B, rank=rank, world_size=world, out_host=out_h, device=dev)[0]
+        y0, y1, _, _ = sifnn_b200.owned_rows(1200, 1200, rank, world)
+        h2d, d2h = (64 * 1200 + 256 * 4800) * 4 * (y1 - y0), 256 * 4800 * 4 * (y1 - y0)   # rank 0's share (upper bound of its result bytes)
         flop_per_step = FWD_GFLOP * 1e9 * nwin / n_gpus
     elif mode == "infer":
         m.eval()

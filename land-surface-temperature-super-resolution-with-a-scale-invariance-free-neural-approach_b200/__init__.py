@@ -14,7 +14,7 @@ from .model import (ModelB_2, DoubleConvolution, UpBlock, ResidualConnection, Do
 from .losses import sr_losses, sr1_losses, sr2_losses, loss_fwd_bwd  # noqa: F401
 from .trainer import Trainer  # noqa: F401
 from .parallel import block_partition, shard_batch, BucketedAllReduce  # noqa: F401
-from .tile import super_resolve_tile, super_resolve_geotiff, window_list  # noqa: F401
+from .tile import super_resolve_tile, super_resolve_tile_host, super_resolve_geotiff, window_list, owned_rows  # noqa: F401
 from .serving import PipelinedInference  # noqa: F401
 from .fit import model_checkpoint, fit, train_epoch, eval_epoch, save_model, load_model, save_metrics  # noqa: F401
 from .dataset import ModisDatasetB, PinnedBatchLoader, read_geotiff, save_geotiff, upsampling  # noqa: F401

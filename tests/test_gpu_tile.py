@@ -93,3 +93,28 @@ def test_tile_from_geotiff_files(tmp_path):
     img, cols, rows, proj, gt = sifnn_b200.read_geotiff(fo)
     assert (rows, cols) == tuple(ndvi.shape) and proj == "EPSG:32631" and gt == gt_ndvi
     assert np.array_equal(img, ref.cpu().numpy())
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+def test_host_sharded_tile_moves_only_owned_rows_and_matches(world):
+    """super_resolve_tile_host over `world` simulated ranks (run one after the other on this GPU, one shared host result buffer) == the
+    whole-tile device function, bit for bit; every rank uploads only its band of window rows."""
+    m = model_mod.ModelB_2(2)
+    m.load_state_dict(load_ckpt("1009"))
+    m = m.cuda().eval()
+    ht, wt = 64 * 5 + 16, 64 * 4       # 5 x 4 full windows + a partial strip that stays 0 (predict.py:95)
+    g = torch.Generator().manual_seed(9)
+    lst = 300 + 8 * torch.rand(ht, wt, generator=g)
+    ndvi = 0.6 + 0.3 * torch.randn(4 * ht, 4 * wt, generator=g)
+    stats = STATS
+    ref = sifnn_b200.super_resolve_tile(m, lst.cuda(), ndvi.cuda(), stats, batch=7).cpu()
+    out = torch.zeros(4 * ht, 4 * wt)
+    covered = 0
+    for r in range(world):
+        y0, y1, wy, wx = sifnn_b200.owned_rows(ht, wt, r, world)
+        covered += wy.numel()
+        assert (y1 - y0) <= ((20 + world - 1) // world + 3) // 4 + 1     # a band of window rows, not the tile
+        _, r0, r1 = sifnn_b200.super_resolve_tile_host(m, lst, ndvi, stats, batch=7, rank=r, world_size=world, out_host=out)
+        assert (r0, r1) == (256 * y0, 256 * y1)
+    assert covered == 20
+    assert torch.equal(out, ref)
