@@ -417,7 +417,7 @@ class PinnedBatchLoader:
     saves 4/5 of the host->device bytes of a step and the host bicubic.
 
     Slot reuse: when the consumer asks for the next batch, an event is recorded on its current CUDA stream for the batch it
-    just had, and the slot is handed back to the workers only after that event has completed, so asynchronous copies out of
+    just had, and the slot is handed back to the workers only once that event has completed (polled, never waited for unless no batch is in flight), so asynchronous copies out of
     the slot (``.to(device, non_blocking=True)``, ``step_host_async``) issued before the next ``next()`` are safe.
     Iteration order follows ``torch.randperm`` with ``seed + epoch`` (or the global generator when seed is None), like
     DataLoader(shuffle=True); the last short batch is kept unless ``drop_last``.  ``rank`` / ``world_size`` shard every epoch's
@@ -555,14 +555,26 @@ class _LoaderIter:
         self.closed = False
         self._dispatch()
 
-    def _dispatch(self):
+    def _dispatch(self, block: bool = False):
+        """Hand free slots to the workers.  A slot whose consumer-side copies may still be running (its event has not completed) is skipped, not
+        waited for: the consumer thread never blocks on the GPU here (round 1 synchronised on the slot it had just released, i.e. on the step
+        it had just launched).  ``block=True`` -- only when the consumer would otherwise have no batch to wait for -- waits for the oldest one."""
         l = self.l
         while self.next_fill < len(self.batches) and self.free:
-            s = self.free.pop(0)
-            ev = l._slots[s]["event"]
-            if ev is not None:
-                ev.synchronize()             # copies out of this slot issued by the consumer have finished
-                l._slots[s]["event"] = None
+            pick = None
+            for i, cand in enumerate(self.free):
+                ev = l._slots[cand]["event"]
+                if ev is None or ev.query():
+                    pick = i
+                    break
+            if pick is None:
+                if not block:
+                    return
+                pick = 0
+                l._slots[self.free[0]]["event"].synchronize()
+            block = False
+            s = self.free.pop(pick)
+            l._slots[s]["event"] = None
             b = self.next_fill
             self.next_fill += 1
             self.slot_of[b] = s
@@ -618,6 +630,8 @@ class _LoaderIter:
             self.close()
             raise StopIteration
         b = self.next_out
+        if b not in self.slot_of:        # every free slot is still being read by the GPU: now (and only now) wait for the oldest
+            self._dispatch(block=True)
         while self.left[b] > 0:
             err = self._collect_one()
             if err is not None:
