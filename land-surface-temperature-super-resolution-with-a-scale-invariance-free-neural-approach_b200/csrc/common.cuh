@@ -86,6 +86,17 @@ int conv3x3_fwd_fs_prepped(const float* in, const float* in2, int K1, const floa
                            int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st, const BnTail* tail = nullptr);
 int conv3x3_dgrad_fs_prepped(const float* dy, const void* wprep, const float* wedge, float* dx, int accumulate, int B, int Cin, int Cout, int H, int W, cudaStream_t st);
 
+// Weight gradient in two halves for the network plan: `*_partials` launches only the main kernel, which leaves per-CTA partial sums
+// [slots][Cout * Cin * 9] in `partial` (*slots_out slots); wgrad_reduce_many then sums the partials of MANY layers in one launch (fixed order,
+// deterministic).  The public sifnn_conv3x3_wgrad_km / _tc do both for one layer.
+int wgrad_km_partials(const float* in, const float* in_scale, const float* in_shift, const float* dy, void* partial, int B, int Cin, int Cout, int H, int W,
+                      cudaStream_t st, int* slots_out);
+int wgrad_tc_partials(const float* in, const float* in_scale, const float* in_shift, const float* dy, void* partial, int B, int Cin, int Cout, int H, int W,
+                      cudaStream_t st, int* slots_out);
+struct ReduceJob { const float* partial; float* out; int n; int slots; };
+constexpr int REDUCE_MAX_JOBS = 20;
+int wgrad_reduce_many(const ReduceJob* jobs, int njobs, cudaStream_t st);
+
 // "do once per device" (cudaFuncSetAttribute is per device; a process may drive several GPUs, possibly from several threads)
 struct PerDeviceOnce {
     unsigned long long mask[2] = {0ull, 0ull};   // up to 128 devices

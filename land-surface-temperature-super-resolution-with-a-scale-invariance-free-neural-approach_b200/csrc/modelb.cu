@@ -108,6 +108,7 @@ struct Workspace {
     float* gR[3];
     float* gU[3];
     void* wgrad_ws;
+    void* wgrad_part[SIFNN_MODELB_NCONV];   // per-layer partial sums of the tensor-core weight gradients (reduced in one launch per backward phase)
     void* wprep_f[SIFNN_MODELB_NCONV];  // hi/lo-split weights per layer, forward layout (tensor-core path; all prepared by ONE launch per pass)
     void* wprep_d[SIFNN_MODELB_NCONV];  // same, data-gradient layout (training only)
     float* wedge_d[SIFNN_MODELB_NCONV]; // fp32 edge taps of the fold + shift data gradient (training only)
@@ -150,8 +151,7 @@ Workspace carve(const Net& n, void* base, int B, int H, int W, int train) {
             const size_t b2 = sifnn_conv3x3_wgrad_tc_workspace(B, n.conv[i].cin, n.conv[i].cout, H >> s, W >> s);
             const size_t b3 = sifnn_conv3x3_wgrad_km_workspace(B, n.conv[i].cin, n.conv[i].cout, H >> s, W >> s);
             if (b > mx) mx = b;
-            if (b2 > mx) mx = b2;
-            if (b3 > mx) mx = b3;
+            w.wgrad_part[i] = c.take<char>(b2 > b3 ? b2 : b3);
         }
         w.wgrad_ws = c.take<char>(mx);
     }
@@ -333,19 +333,33 @@ extern "C" int sifnn_modelb_backward(const sifnn_modelb_cfg* cfg, const float* p
     auto sc = [&](int i) { return w.scale + n.bn_off[i]; };
     auto sh = [&](int i) { return w.shift + n.bn_off[i]; };
     // gradient of conv i's weights; input = raw[aff] through BN+ReLU, or a plain tensor
+    // Tensor-core weight gradients leave per-CTA partials in the layer's own buffer; one launch per backward phase sums them all (the 16 small
+    // reduce launches were ~5 us each on the critical path of the step).
+    sifnn::ReduceJob rjobs[SIFNN_MODELB_NCONV];
+    int nrjobs = 0;
+    auto flush_reduces = [&]() -> int {
+        const int rc = sifnn::wgrad_reduce_many(rjobs, nrjobs, st);
+        nrjobs = 0;
+        return rc;
+    };
     auto wgrad = [&](int i, const float* in, int aff, const float* g) -> int {
         const ConvDesc& c = n.conv[i];
+        const float* isc = aff >= 0 ? sc(aff) : nullptr;
+        const float* ish = aff >= 0 ? sh(aff) : nullptr;
         // 16-bit K-major kernel (wgrad_km.cu) except for wide inputs on large images, where the TF32 kernel's bigger channel blocks win
         // (profiles/r2w_profile_wgrad.log: 64->32 @128 and 128->64 @64 are 4-10 % faster on wgrad_tc, everything else 1.0-2.1x faster on km)
         const bool km_wins = !(c.cin >= 64 && ws[c.level] >= 64);
-        if (tc_enabled() && i != 17 && km_wins && sifnn_conv3x3_wgrad_km_supported(c.cin, c.cout, hs[c.level], ws[c.level]))
-            return sifnn_conv3x3_wgrad_km(in, aff >= 0 ? sc(aff) : nullptr, aff >= 0 ? sh(aff) : nullptr, g, grads + n.w_off[i], w.wgrad_ws, B, c.cin,
-                                          c.cout, hs[c.level], ws[c.level], stream);
-        if (tc_enabled() && i != 17 && sifnn_conv3x3_wgrad_tc_supported(c.cin, c.cout, hs[c.level], ws[c.level]))
-            return sifnn_conv3x3_wgrad_tc(in, aff >= 0 ? sc(aff) : nullptr, aff >= 0 ? sh(aff) : nullptr, g, grads + n.w_off[i], w.wgrad_ws, B, c.cin,
-                                          c.cout, hs[c.level], ws[c.level], stream);
-        return sifnn_conv3x3_wgrad(in, aff >= 0 ? sc(aff) : nullptr, aff >= 0 ? sh(aff) : nullptr, g, grads + n.w_off[i],
-                                   i == 17 ? grads + n.bias_off : nullptr, w.wgrad_ws, B, c.cin, c.cout, hs[c.level], ws[c.level], stream);
+        int slots = 0;
+        if (tc_enabled() && i != 17 && km_wins && sifnn_conv3x3_wgrad_km_supported(c.cin, c.cout, hs[c.level], ws[c.level])) {
+            SIFNN_TRY(sifnn::wgrad_km_partials(in, isc, ish, g, w.wgrad_part[i], B, c.cin, c.cout, hs[c.level], ws[c.level], st, &slots));
+        } else if (tc_enabled() && i != 17 && sifnn_conv3x3_wgrad_tc_supported(c.cin, c.cout, hs[c.level], ws[c.level])) {
+            SIFNN_TRY(sifnn::wgrad_tc_partials(in, isc, ish, g, w.wgrad_part[i], B, c.cin, c.cout, hs[c.level], ws[c.level], st, &slots));
+        } else {
+            return sifnn_conv3x3_wgrad(in, isc, ish, g, grads + n.w_off[i], i == 17 ? grads + n.bias_off : nullptr, w.wgrad_ws, B, c.cin, c.cout, hs[c.level],
+                                       ws[c.level], stream);
+        }
+        rjobs[nrjobs++] = sifnn::ReduceJob{static_cast<const float*>(w.wgrad_part[i]), grads + n.w_off[i], c.cout * c.cin * 9, slots};
+        return 0;
     };
     auto dgrad_kind = [&](int i) {
         const ConvDesc& c = n.conv[i];
@@ -415,6 +429,7 @@ extern "C" int sifnn_modelb_backward(const sifnn_modelb_cfg* cfg, const float* p
             SIFNN_TRY(dgrad(c0, w.g[c0], w.gU[k], 0));
             SIFNN_TRY(sifnn_upcat_bwd(w.gU[k], w.g[low], w.g[skip], B, n.conv[low].cout, n.conv[skip].cout, hs[ll], ws[ll], stream));
         }
+        SIFNN_TRY(flush_reduces());   // decoder gradients complete (the first all-reduce bucket of a data-parallel step)
     }
     if (phase == 0 || phase == 2) {
         for (int k = 2; k >= 0; --k) {  // db3, db2, db1
@@ -436,6 +451,7 @@ extern "C" int sifnn_modelb_backward(const sifnn_modelb_cfg* cfg, const float* p
         SIFNN_TRY(dgrad(1, w.g[1], w.g[0], 0));
         SIFNN_TRY(bnbwd(0, w.g[0], w.g[0]));
         SIFNN_TRY(wgrad(0, x, -1, w.g[0]));
+        SIFNN_TRY(flush_reduces());
     }
     return 0;
 }

@@ -381,14 +381,15 @@ extern "C" size_t sifnn_conv3x3_wgrad_km_workspace(int B, int Cin, int Cout, int
     return (size_t)2 * sifnn::num_sms() * Cout * Cin * 9 * sizeof(float);   // two partial slots per CTA when dy rows are paired (16 output channels per CTA)
 }
 
-extern "C" int sifnn_conv3x3_wgrad_km(const float* in, const float* in_scale, const float* in_shift, const float* dy, float* dw, void* workspace,
-                                      int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream) {
-    SIFNN_REQUIRE(in && dy && dw && workspace, "conv3x3_wgrad_km: null pointer");
+namespace sifnn {
+
+int wgrad_km_partials(const float* in, const float* in_scale, const float* in_shift, const float* dy, void* workspace, int B, int Cin, int Cout, int H, int W,
+                      cudaStream_t st, int* slots_out) {
+    SIFNN_REQUIRE(in && dy && workspace, "conv3x3_wgrad_km: null pointer");
     SIFNN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "conv3x3_wgrad_km: in_scale/in_shift must both be set or both NULL");
     SIFNN_REQUIRE(B > 0 && B <= 65535 && sifnn_conv3x3_wgrad_km_supported(Cin, Cout, H, W), "conv3x3_wgrad_km: unsupported shape Cin=%d Cout=%d H=%d W=%d", Cin,
                   Cout, H, W);
     SIFNN_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0, "conv3x3_wgrad_km: tensors must be 16-byte aligned");
-    cudaStream_t st = sifnn::as_stream(stream);
     KmArgs a{};
     a.in_scale = in_scale; a.in_shift = in_shift; a.partial = static_cast<float*>(workspace);
     a.B = B; a.K = Cin; a.O = Cout; a.H = H; a.W = W;
@@ -406,7 +407,57 @@ extern "C" int sifnn_conv3x3_wgrad_km(const float* in, const float* in_scale, co
     else if (ci == 16 && co == 32) rc = launch_km<16, 32, 4>(in, dy, a, S, affine, st);
     else rc = launch_km<32, 32, 2>(in, dy, a, S, affine, st);
     SIFNN_TRY(rc);
+    *slots_out = co == 16 ? 2 * S : S;
+    return 0;
+}
+
+// out[i] = sum_s partial[s][i] for up to REDUCE_MAX_JOBS (layer) jobs in one launch; block -> job by a prefix table
+struct ReduceTable { ReduceJob j[REDUCE_MAX_JOBS]; int first_block[REDUCE_MAX_JOBS + 1]; int njobs; };
+__global__ void __launch_bounds__(1024) wgrad_reduce_many_kernel(const ReduceTable t) {
+    __shared__ float red[32][33];
+    int k = 0;
+    while (k + 1 < t.njobs && (int)blockIdx.x >= t.first_block[k + 1]) ++k;
+    const ReduceJob job = t.j[k];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = ((int)blockIdx.x - t.first_block[k]) * 32 + tx;
+    float acc = 0.f;
+    if (i < job.n)
+        for (int s = ty; s < job.slots; s += 32) acc += __ldg(job.partial + (size_t)s * job.n + i);
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && i < job.n) {
+        float v = red[0][tx];
+#pragma unroll
+        for (int r = 1; r < 32; ++r) v += red[r][tx];
+        job.out[i] = v;
+    }
+}
+
+int wgrad_reduce_many(const ReduceJob* jobs, int njobs, cudaStream_t st) {
+    if (njobs <= 0) return 0;
+    SIFNN_REQUIRE(njobs <= REDUCE_MAX_JOBS, "wgrad_reduce_many: too many jobs (%d)", njobs);
+    ReduceTable t{};
+    int blocks = 0;
+    for (int k = 0; k < njobs; ++k) {
+        t.j[k] = jobs[k];
+        t.first_block[k] = blocks;
+        blocks += (jobs[k].n + 31) / 32;
+    }
+    t.first_block[njobs] = blocks;
+    t.njobs = njobs;
+    wgrad_reduce_many_kernel<<<blocks, 1024, 0, st>>>(t);
+    return check_launch("wgrad_reduce_many_kernel");
+}
+
+}  // namespace sifnn
+
+extern "C" int sifnn_conv3x3_wgrad_km(const float* in, const float* in_scale, const float* in_shift, const float* dy, float* dw, void* workspace,
+                                      int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(dw, "conv3x3_wgrad_km: null pointer");
+    cudaStream_t st = sifnn::as_stream(stream);
+    int S = 0;
+    SIFNN_TRY(sifnn::wgrad_km_partials(in, in_scale, in_shift, dy, workspace, B, Cin, Cout, H, W, st, &S));
     const int n = Cout * Cin * 9;
-    wgrad_km_reduce_kernel<<<(n + 31) / 32, 1024, 0, st>>>(a.partial, dw, n, co == 16 ? 2 * S : S);
+    wgrad_km_reduce_kernel<<<(n + 31) / 32, 1024, 0, st>>>(static_cast<const float*>(workspace), dw, n, S);
     return sifnn::check_launch("wgrad_km_reduce_kernel");
 }

@@ -407,14 +407,14 @@ extern "C" size_t sifnn_conv3x3_wgrad_tc_workspace(int B, int Cin, int Cout, int
     return (size_t)wtc_S(B, Cin, H, W) * Cout * Cin * 9 * sizeof(float);
 }
 
-extern "C" int sifnn_conv3x3_wgrad_tc(const float* in, const float* in_scale, const float* in_shift, const float* dy, float* dw, void* workspace,
-                                      int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream) {
-    SIFNN_REQUIRE(in && dy && dw && workspace, "conv3x3_wgrad_tc: null pointer");
+namespace sifnn {
+int wgrad_tc_partials(const float* in, const float* in_scale, const float* in_shift, const float* dy, void* workspace, int B, int Cin, int Cout, int H, int W,
+                      cudaStream_t st, int* slots_out) {
+    SIFNN_REQUIRE(in && dy && workspace, "conv3x3_wgrad_tc: null pointer");
     SIFNN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "conv3x3_wgrad_tc: in_scale/in_shift must both be set or both NULL");
     SIFNN_REQUIRE(B > 0 && B <= 65535 && sifnn_conv3x3_wgrad_tc_supported(Cin, Cout, H, W), "conv3x3_wgrad_tc: unsupported shape Cin=%d Cout=%d H=%d W=%d", Cin,
                   Cout, H, W);
     SIFNN_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0, "conv3x3_wgrad_tc: tensors must be 16-byte aligned");
-    cudaStream_t st = sifnn::as_stream(stream);
     WtcArgs a{};
     a.in_scale = in_scale; a.in_shift = in_shift; a.partial = static_cast<float*>(workspace);
     a.B = B; a.K = Cin; a.O = Cout; a.H = H; a.W = W;
@@ -436,7 +436,18 @@ extern "C" int sifnn_conv3x3_wgrad_tc(const float* in, const float* in_scale, co
         }
     }
     SIFNN_TRY(rc);
+    *slots_out = S;
+    return 0;
+}
+}  // namespace sifnn
+
+extern "C" int sifnn_conv3x3_wgrad_tc(const float* in, const float* in_scale, const float* in_shift, const float* dy, float* dw, void* workspace,
+                                      int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(dw, "conv3x3_wgrad_tc: null pointer");
+    cudaStream_t st = sifnn::as_stream(stream);
+    int S = 0;
+    SIFNN_TRY(sifnn::wgrad_tc_partials(in, in_scale, in_shift, dy, workspace, B, Cin, Cout, H, W, st, &S));
     const int n = Cout * Cin * 9;
-    wgrad_tc_reduce_kernel<<<(n + 31) / 32, 1024, 0, st>>>(a.partial, dw, n, S);
+    wgrad_tc_reduce_kernel<<<(n + 31) / 32, 1024, 0, st>>>(static_cast<const float*>(workspace), dw, n, S);
     return sifnn::check_launch("wgrad_tc_reduce_kernel");
 }

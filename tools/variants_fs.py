@@ -9,6 +9,9 @@ from sifnn_b200 import _lib
 lib = sifnn_b200.load()
 kind = int(os.environ.get('KIND', '2'))
 lib.sifnn_conv3x3_fs_config(kind, 0)
+lib.sifnn_conv3x3_ff_config(kind, 0)
+if os.environ.get("NARROW") == "1":      # M = 64 fold + shift path for the 64- / 32-pixel-wide levels, next to the full-fold kernel
+    lib.sifnn_conv3x3_fs_narrow(1)
 B = 32
 for sh in (sys.argv[1:] or ["16x16x256", "32x16x256", "64x32x128"]):
     ci, co, hw = (int(v) for v in sh.split("x"))
@@ -27,6 +30,16 @@ for sh in (sys.argv[1:] or ["16x16x256", "32x16x256", "64x32x128"]):
         "dgrad": lambda: _lib.call("sifnn_conv3x3_dgrad_fs", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), 0, wprep.data_ptr(), B, ci, co, hw, hw, st),
         "dgrad+acc": lambda: _lib.call("sifnn_conv3x3_dgrad_fs", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), 1, wprep.data_ptr(), B, ci, co, hw, hw, st),
     }
+    if lib.sifnn_conv3x3_ff_supported(ci, co, hw, hw) and ci <= 64:
+        fns["ff affine+stats"] = lambda: _lib.call("sifnn_conv3x3_fwd_ff", x.data_ptr(), sc.data_ptr(), shf.data_ptr(), w.data_ptr(), out.data_ptr(), stats.data_ptr(), wprep.data_ptr(), B, ci, co, hw, hw, st)
+    if lib.sifnn_conv3x3_ff_supported(co, ci, hw, hw):
+        fns["ff dgrad"] = lambda: _lib.call("sifnn_conv3x3_dgrad_ff", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), 0, wprep.data_ptr(), B, ci, co, hw, hw, st)
+    if not lib.sifnn_conv3x3_fs_supported(ci, co, hw, hw):
+        for k in ("plain", "affine", "stats", "affine+stats"):
+            fns.pop(k)
+    if not lib.sifnn_conv3x3_fs_supported(co, ci, hw, hw):
+        for k in ("dgrad", "dgrad+acc"):
+            fns.pop(k)
     row = []
     for name, fn in fns.items():
         fn(); torch.cuda.synchronize()
