@@ -3,6 +3,7 @@
 // bicubic x4 + concat input stage.  All kernels are streaming: coalesced (float4 where
 // alignment allows), grid-stride, grid sized as a multiple of the SM count.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -90,12 +91,16 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const float* __restrict__ gamma, const double* __restrict__ sums,
-                                                                float* dx, float* dgamma, float* dbeta, int C, int HW, double inv_n) {
-    const int c = blockIdx.y, b = blockIdx.z;
+                                                                float* dx, float* dgamma, float* dbeta, int C, int HW, double inv_n, int reverse) {
+    // reverse = 1: walk the tensors from the end.  The reduce pass that ran just before read dY and raw front to back, so their tails are what the
+    // 126 MB L2 still holds; on the 256^2 layers (2 x 134 MB) a front-to-back second pass would miss everywhere.
+    const int c = reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int b = reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    const int bx = reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
     const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
     const float m1 = (float)(sums[c] * inv_n), m2 = (float)(sums[C + c] * inv_n);
     const float gi = gamma[c] * is;
-    if (b == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (b == 0 && bx == 0 && threadIdx.x == 0) {
         if (dbeta) dbeta[c] = (float)sums[c];
         if (dgamma) dgamma[c] = (float)sums[C + c];
     }
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
     const float4* x4 = reinterpret_cast<const float4*>(raw + base);
     float4* o4 = reinterpret_cast<float4*>(dx + base);
     const int n4 = HW >> 2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    for (int i = bx * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
         const float4 g = g4[i], x = __ldg(x4 + i);
         const float gv[4] = {g.x, g.y, g.z, g.w}, xv[4] = {x.x, x.y, x.z, x.w};
         float ov[4];
@@ -557,8 +562,10 @@ extern "C" int sifnn_bn_relu_bwd_apply(const float* dY, const float* raw, const 
     SIFNN_REQUIRE(dY && raw && scale && shift && save_mean && save_invstd && gamma && sums && dx, "bn_relu_bwd_apply: null pointer");
     SIFNN_REQUIRE(B > 0 && C > 0 && HW > 0 && HW % 4 == 0 && B <= 65535 && C <= 65535, "bn_relu_bwd_apply: bad shape (HW must be a multiple of 4)");
     dim3 grid(bn_bwd_chunks(B, C, HW), C, B);
+    static int reverse = -1;   // SIFNN_BN_REVERSE=0 restores the front-to-back walk (A/B runs)
+    if (reverse < 0) { const char* e = getenv("SIFNN_BN_REVERSE"); reverse = (e && e[0] == '0') ? 0 : 1; }
     bn_relu_bwd_apply_kernel<<<grid, 256, 0, sifnn::as_stream(stream)>>>(dY, raw, scale, shift, save_mean, save_invstd, gamma, sums, dx, dgamma, dbeta, C, HW,
-                                                                           1.0 / ((double)B * HW));
+                                                                           1.0 / ((double)B * HW), reverse);
     return sifnn::check_launch("bn_relu_bwd_apply_kernel");
 }
 
