@@ -180,12 +180,19 @@ __device__ __forceinline__ void fs_convert_pixel(const float* raw, int rpx, unsi
     for (int q = 0; q < 2; ++q) {
         if constexpr (KIND != 1) {
             uint32_t hp[4], lp[4];
+            float scv[8], shv[8];   // the eight channels' BatchNorm scale / shift as four 16-byte broadcast loads instead of sixteen scalar ones
+            if (AFFINE) {
+                const float4 s0 = *reinterpret_cast<const float4*>(sc + 8 * q), s1 = *reinterpret_cast<const float4*>(sc + 8 * q + 4);
+                const float4 h0 = *reinterpret_cast<const float4*>(sh + 8 * q), h1 = *reinterpret_cast<const float4*>(sh + 8 * q + 4);
+                scv[0] = s0.x; scv[1] = s0.y; scv[2] = s0.z; scv[3] = s0.w; scv[4] = s1.x; scv[5] = s1.y; scv[6] = s1.z; scv[7] = s1.w;
+                shv[0] = h0.x; shv[1] = h0.y; shv[2] = h0.z; shv[3] = h0.w; shv[4] = h1.x; shv[5] = h1.y; shv[6] = h1.z; shv[7] = h1.w;
+            }
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
                 float t0 = raw[(8 * q + e) * rpx], t1 = raw[(8 * q + e + 1) * rpx];
                 if (AFFINE) {
-                    t0 = sifnn::act_affine_relu(t0, sc[8 * q + e], sh[8 * q + e]);
-                    t1 = sifnn::act_affine_relu(t1, sc[8 * q + e + 1], sh[8 * q + e + 1]);
+                    t0 = sifnn::act_affine_relu(t0, scv[e], shv[e]);
+                    t1 = sifnn::act_affine_relu(t1, scv[e + 1], shv[e + 1]);
                 }
                 if constexpr (KIND == 0) {
                     const uint32_t h = fs_pack_bf16x2(t0, t1);
@@ -250,7 +257,9 @@ __global__ void __launch_bounds__(fs_threads(PAD, NG), 1) conv3x3_fs_kernel(cons
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = a.H, W = a.W;
-    const int Wt = W < 128 ? W : 128;        // pixels of a row piece (MM = 64 serves the 64- and 32-pixel-wide levels: one image row per MMA, junk rows beyond)
+    // pixels of a row piece (MM = 64 serves the 64- and 32-pixel-wide levels: one image row per MMA, junk rows beyond).  A compile-time constant in the
+    // M = 128 form, so the channel stride of the raw stage (rpx) folds into the immediate offsets of the transformers' shared-memory loads
+    const int Wt = (MM == 128) ? 128 : (W < 128 ? W : 128);
     const int T = W / Wt;
     const int rpx = Wt + 8;                    // staged pixels per channel of a raw box: x0 - 4 .. x0 + Wt + 3
     const uint32_t raw_bytes = (uint32_t)(KC * rpx * 4);
