@@ -368,14 +368,17 @@ def inference_subrecord(m, dev, steps_small=50):
         dt = timed_events(step, steps, warm=2)
         out_h = [torch.empty((bsz, 1, 256, 256), dtype=torch.float32).pin_memory() for _ in range(2)]
         pipe = sifnn_b200.PipelinedInference(m)
-        for i in range(2):
+        for i in range(8 if bsz <= 32 else 2):
             pipe.submit(*host[i % nbuf], out_h[i % 2])
         pipe.flush(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(steps):
-            pipe.submit(*host[i % nbuf], out_h[i % 2])
-        pipe.flush(); torch.cuda.synchronize()
-        e2e = (time.perf_counter() - t0) / steps
+        windows = []   # three timed windows, the median is reported (a 13 ms window at batch 1 is at the mercy of one host hiccup)
+        for _ in range(3 if bsz <= 32 else 1):
+            t0 = time.perf_counter()
+            for i in range(steps):
+                pipe.submit(*host[i % nbuf], out_h[i % 2])
+            pipe.flush(); torch.cuda.synchronize()
+            windows.append((time.perf_counter() - t0) / steps)
+        e2e = sorted(windows)[len(windows) // 2]
         rows.append({"batch": bsz, "mpix_s_device": bsz * PATCH_MPIX / dt, "mpix_s_e2e": bsz * PATCH_MPIX / e2e, "ms_per_batch": dt * 1e3,
                      "h2d_bytes_per_batch": bsz * (64 * 64 + 256 * 256) * 4, "d2h_bytes_per_batch": bsz * 256 * 256 * 4,
                      "launch": "cuda-graph replay" if bsz <= 8 else "eager, chunks of 32"})
