@@ -298,7 +298,7 @@ def kernel_rooflines(batch, fp32_peak, hbm_gbs, bf16_tflops, tf32_tflops, forwar
                     add("conv3x3_tc_kernel (dgrad, TF32 split, round 1)", "tensor32", timed(lambda: _lib.call("sifnn_conv3x3_dgrad_tc", P(dy), P(w), P(dx), 0, P(wprep), batch, ci, co, hw, hw, st)), fl, by)
                 else:
                     add("dgrad_from1_kernel 16->1 (dgrad, SIMT)", "fp32", timed(lambda: _lib.call("sifnn_conv3x3_dgrad", P(dy), P(w), P(dx), 0, batch, ci, co, hw, hw, st)), fl, by)
-            if use_tc and co > 1 and not (ci >= 64 and hw >= 64) and lib.sifnn_conv3x3_wgrad_km_supported(ci, co, hw, hw):   # the plan's rule (modelb.cu wgrad)
+            if use_tc and co > 1 and lib.sifnn_conv3x3_wgrad_km_supported(ci, co, hw, hw):   # the plan's rule (modelb.cu wgrad)
                 add("wgrad_km_kernel (BF16 split)", "tensor16", timed(lambda: _lib.call("sifnn_conv3x3_wgrad_km", P(x), None, None, P(dy), P(dw), P(ws), batch, ci, co, hw, hw, st)), fl, by)
             elif use_tc and lib.sifnn_conv3x3_wgrad_tc_supported(ci, co, hw, hw):
                 add("wgrad_tc_kernel (TF32 split)", "tensor32", timed(lambda: _lib.call("sifnn_conv3x3_wgrad_tc", P(x), None, None, P(dy), P(dw), P(ws), batch, ci, co, hw, hw, st)), fl, by)

@@ -346,9 +346,9 @@ extern "C" int sifnn_modelb_backward(const sifnn_modelb_cfg* cfg, const float* p
         const ConvDesc& c = n.conv[i];
         const float* isc = aff >= 0 ? sc(aff) : nullptr;
         const float* ish = aff >= 0 ? sh(aff) : nullptr;
-        // 16-bit K-major kernel (wgrad_km.cu) except for wide inputs on large images, where the TF32 kernel's bigger channel blocks win
-        // (profiles/r2w_profile_wgrad.log: 64->32 @128 and 128->64 @64 are 4-10 % faster on wgrad_tc, everything else 1.0-2.1x faster on km)
-        const bool km_wins = !(c.cin >= 64 && ws[c.level] >= 64);
+        // 16-bit K-major kernel (wgrad_km.cu) wherever it takes the shape; the round-1 TF32 kernel otherwise.  (With the deeper raw ring km ties or
+        // beats wgrad_tc on the wide layers too: 64->32 @128 118 vs 125 us, 128->64 @64 127 vs 126, 64->32 @64 42 vs 42; profiles/r2za_profile_wgrad.log.)
+        const bool km_wins = true;
         int slots = 0;
         if (tc_enabled() && i != 17 && km_wins && sifnn_conv3x3_wgrad_km_supported(c.cin, c.cout, hs[c.level], ws[c.level])) {
             SIFNN_TRY(sifnn::wgrad_km_partials(in, isc, ish, g, w.wgrad_part[i], B, c.cin, c.cout, hs[c.level], ws[c.level], st, &slots));
