@@ -58,6 +58,7 @@ struct FfArgs {
     int nrows;    // B * H
     int K1;       // channels that come from the first tensor map (== K without a second source)
     unsigned long long* trace;   // debug (sifnn_conv3x3_ff_trace): clock64 stamps of CTA (0,0), [event][step], 256 steps per event
+    int epi_spin; // epilogue waits for an accumulator by polling (1) or suspended (0)
     int ablate;   // debug (sifnn_conv3x3_ff_debug): 1 no MMAs, 2 no epilogue math, 4 no TMEM loads, 8 no transform, 16 no global stores, 32 loads hit L2
 };
 
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs 
 #pragma unroll
             for (int g = 0; g < NG; ++g, ++seq) {
                 const int slot = seq % FF_NSLOT;
-                mbar_wait_spin(acc_full + slot, (seq / FF_NSLOT) & 1);
+                if (a.epi_spin) mbar_wait_spin(acc_full + slot, (seq / FF_NSLOT) & 1);
+                else mbar_wait(acc_full + slot, (seq / FF_NSLOT) & 1);
                 tc_fence_after();
                 if (tid == 0 && g == 0) FF_STAMP(7, step);
                 const uint32_t tcol = tlane + slot * FF_N;
@@ -597,6 +599,7 @@ int run_ff(const sifnn::BnTail* tail, int pad, const float* in, const float* in2
     FfArgs a{};
     a.in_scale = in_scale; a.in_shift = in_shift; a.wprep = static_cast<const unsigned char*>(wprep); a.out = out; a.stats = stats;
     if (tail && stats) a.tail = *tail;
+    { static int spin = -1; if (spin < 0) { const char* e = getenv("SIFNN_FF_EPI_SPIN"); spin = e ? atoi(e) : 0; } a.epi_spin = spin; }   // default suspended: on the 64- / 32-pixel levels the epilogue waits for the MMAs, polling only took issue slots (4.221 -> 4.215 ms)
     a.B = B; a.K = K; a.O = O; a.H = H; a.W = W; a.accumulate = accumulate ? 1 : 0;
     a.G = W < 128 ? 128 / W : 1;
     a.nrows = B * H;
