@@ -280,7 +280,7 @@ def kernel_rooflines(batch, fp32_peak, hbm_gbs, bf16_tflops, tf32_tflops, forwar
         by = 4.0 * batch * (ci + co) * hw * hw
         P = lambda t: t.data_ptr()
         # forward
-        if use_tc and lib.sifnn_conv3x3_fs_supported(ci, co, hw, hw):
+        if use_tc and (lib.sifnn_conv3x3_fs_supported(ci, co, hw, hw) or (hw == 64 and ci == 32 and co in (32, 64))):   # + the plan's M = 64 forward layers
             add("conv3x3_fs_kernel (fwd, FP16 split)", "tensor16", timed(lambda: _lib.call("sifnn_conv3x3_fwd_fs", P(x), None, None, P(w), P(y), None, P(wprep), batch, ci, co, hw, hw, st)), fl, by)
         elif use_tc and lib.sifnn_conv3x3_ff_supported(ci, co, hw, hw):
             add("conv3x3_ff_kernel (fwd, FP16 split)", "tensor16", timed(lambda: _lib.call("sifnn_conv3x3_fwd_ff", P(x), None, None, P(w), P(y), None, P(wprep), batch, ci, co, hw, hw, st)), fl, by)

@@ -79,6 +79,7 @@ int conv3x3_dgrad_ff_prepped(const float* dy, const void* wprep, float* dx, int 
 // Fold + shift tensor-core convolution for widths that are multiples of 128 (csrc/conv3x3_fs.cu): ky in the MMA's N dimension, kx through shifted
 // operand views, rolling row sums in the epilogue; complete data gradient (padding adjoint included).
 bool conv3x3_fs_supported(int K, int O, int H, int W);
+bool conv3x3_fs_fwd_preferred(int K, int O, int H, int W);   // forward only: also the 64-pixel-level shapes where the M = 64 form beats the full-fold kernel
 size_t conv3x3_fs_wedge_bytes(int K, int O);
 int fs_prep(const float* const* w, void* const* wprep, float* const* wedge, const int* K, const int* O, const int* w_so, const int* w_sk, const int* flip, int n,
             cudaStream_t st);

@@ -633,6 +633,9 @@ int dispatch_fs1(int pad, bool affine, bool stats, const FsArgs& a, const CUtens
     return stats ? dispatch_fs2<KIND, 0, false, true>(a, tm1, tm2, NG, gx, gy, st) : dispatch_fs2<KIND, 0, false, false>(a, tm1, tm2, NG, gx, gy, st);
 }
 
+// Forward shapes of the 64-pixel level that the M = 64 form wins against the full-fold kernel (tools/variants_fs.py, affine + statistics, B = 32):
+// 32 -> 32 @64 33.0 vs 41.1 us, 32 -> 64 @64 51.8 vs 56.8 us.  (64 input channels, the 32-pixel level and every data gradient stay on conv3x3_ff.)
+bool fs_fwd_narrow_wins(int K, int O, int H, int W) { return W == 64 && K == 32 && (O == 32 || O == 64) && H >= 1; }
 bool fs_shape_ok(int K, int O, int H, int W) {
     return ((W % 128 == 0 && W >= 128 && W <= 4096) || ((W == 64 || W == 32) && fs_narrow())) && (K % 16 == 0) && K >= 16 && K <= FS_MAX_K && (O % 16 == 0) && O >= 16 && O <= 128 && (O == 16 || O % 32 == 0) && H >= 1;
 }
@@ -645,7 +648,7 @@ int fs_groups(int K, int O, int kind) {   // output groups of 16 channels per CT
 
 int run_fs(const sifnn::BnTail* tail, int pad, const float* in, const float* in2, int K1, const float* in_scale, const float* in_shift, const void* wprep, const float* wedge, float* out,
            double* stats, int accumulate, int B, int K, int O, int H, int W, cudaStream_t st) {
-    SIFNN_REQUIRE(fs_shape_ok(K, O, H, W), "conv3x3_fs: unsupported shape K=%d O=%d H=%d W=%d", K, O, H, W);
+    SIFNN_REQUIRE(fs_shape_ok(K, O, H, W) || (pad == 0 && fs_fwd_narrow_wins(K, O, H, W)), "conv3x3_fs: unsupported shape K=%d O=%d H=%d W=%d", K, O, H, W);
     const int kind = sifnn::tc_split_kind(pad);
     SIFNN_REQUIRE(!(pad == 1 && kind == 2), "conv3x3_fs: the FP16 split is for the forward form only (gradients can be tiny)");
     const int KC = (kind == 1) ? 8 : 16;
@@ -734,6 +737,7 @@ __global__ void __launch_bounds__(256) fs_prep_kernel(const __grid_constant__ Fs
 namespace sifnn {
 
 bool conv3x3_fs_supported(int K, int O, int H, int W) { return fs_enabled() && fs_shape_ok(K, O, H, W); }
+bool conv3x3_fs_fwd_preferred(int K, int O, int H, int W) { return fs_enabled() && (fs_shape_ok(K, O, H, W) || fs_fwd_narrow_wins(K, O, H, W)); }
 // bytes of the edge-weight table of a data-gradient launch (K = dy channels, O = dx channels)
 size_t conv3x3_fs_wedge_bytes(int K, int O) { return (size_t)2 * K * 3 * O * sizeof(float); }
 
@@ -772,7 +776,7 @@ extern "C" int sifnn_conv3x3_fwd_fs(const float* in, const float* in_scale, cons
                                     int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream) {
     SIFNN_REQUIRE(in && w && out && wprep, "conv3x3_fwd_fs: null pointer");
     SIFNN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "conv3x3_fwd_fs: in_scale/in_shift must both be set or both NULL");
-    SIFNN_REQUIRE(fs_shape_ok(Cin, Cout, H, W) && B > 0 && B <= 65535, "conv3x3_fwd_fs: unsupported shape Cin=%d Cout=%d H=%d W=%d", Cin, Cout, H, W);
+    SIFNN_REQUIRE((fs_shape_ok(Cin, Cout, H, W) || fs_fwd_narrow_wins(Cin, Cout, H, W)) && B > 0 && B <= 65535, "conv3x3_fwd_fs: unsupported shape Cin=%d Cout=%d H=%d W=%d", Cin, Cout, H, W);
     cudaStream_t st = sifnn::as_stream(stream);
     const int K = Cin, O = Cout, so = Cin * 9, sk = 9, flip = 0;
     SIFNN_TRY(sifnn::fs_prep(&w, &wprep, nullptr, &K, &O, &so, &sk, &flip, 1, st));

@@ -75,9 +75,9 @@ bool tc_enabled() {
 //   FS  fold + shift (conv3x3_fs.cu): widths that are multiples of 128;  FF  full fold (conv3x3_ff.cu): 32- and 64-pixel-wide levels;
 //   TC  round-1 tcgen05 kernels (any other eligible shape, more than 64 input channels);  SIMT  fp32 direct convolution.
 enum ConvKind { KIND_SIMT = 0, KIND_TC = 1, KIND_FF = 2, KIND_FS = 3 };
-ConvKind conv_kind(int K, int O, int H, int W, bool tc_ok) {
+ConvKind conv_kind(int K, int O, int H, int W, bool tc_ok, bool forward = false) {
     if (!tc_enabled()) return KIND_SIMT;
-    if (sifnn::conv3x3_fs_supported(K, O, H, W)) return KIND_FS;
+    if (forward ? sifnn::conv3x3_fs_fwd_preferred(K, O, H, W) : sifnn::conv3x3_fs_supported(K, O, H, W)) return KIND_FS;
     if (sifnn::conv3x3_ff_supported(K, O, H, W)) return KIND_FF;
     return tc_ok ? KIND_TC : KIND_SIMT;
 }
@@ -232,7 +232,7 @@ extern "C" int sifnn_modelb_forward(const sifnn_modelb_cfg* cfg, const float* pa
     auto fwd_kind = [&](int i) {
         const ConvDesc& c = n.conv[i];
         const bool tc_ok = c.cout <= 64 && sifnn_conv3x3_tc_supported(c.cin, c.cout, hs[c.level], ws[c.level]) != 0;
-        return conv_kind(c.cin, c.cout, hs[c.level], ws[c.level], tc_ok);
+        return conv_kind(c.cin, c.cout, hs[c.level], ws[c.level], tc_ok, true);
     };
     {
         sifnn::TcPrepJob jobs[SIFNN_MODELB_NCONV];
