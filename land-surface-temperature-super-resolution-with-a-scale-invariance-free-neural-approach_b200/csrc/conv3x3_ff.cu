@@ -39,7 +39,7 @@ constexpr int FF_CS = 4;             // output channels per epilogue thread
 constexpr int FF_N = 144;            // MMA N = TMEM columns of one accumulator slot: (ky, kx, o) = 9 x 16
 constexpr int FF_NSLOT = 3;
 constexpr int FF_MAX_STRIP = 64;     // output rows per strip when a row has two tiles (bounds the carry buffers)
-constexpr int FF_MAX_K = 64;         // input channels per launch
+constexpr int FF_MAX_K = 128;        // input channels per launch (more than 64: one output group per CTA and 16-bit splits only, see run_ff)
 constexpr int FF_W_TILE = 2 * FF_N * 16;   // bytes of one (hi or lo) weight tile of a chunk: [2 q][144 rows][16 B]
 constexpr int FF_A_TILE = 2 * 128 * 16;    // bytes of one (hi or lo) activation tile of a chunk: [2 q][128 pixels][16 B]
 
@@ -585,7 +585,11 @@ int dispatch_ff1(int pad, bool affine, bool stats, const FfArgs& a, const CUtens
 }
 
 bool ff_shape_ok(int K, int O, int H, int W) {
-    return (W == 32 || W == 64 || W == 128 || W == 256) && (K % 16 == 0) && K >= 16 && K <= FF_MAX_K && (O % 16 == 0) && O >= 16 && O <= 128 && H >= 1;
+    // 65..128 input channels: the resident weights (8 chunks) only fit beside the operand ring with one output group per CTA and 16-byte-per-row
+    // 16-bit tiles; the TF32 split (twice the chunks) stays at 64
+    const bool any_tf32 = sifnn::tc_split_kind(0) == 1 || sifnn::tc_split_kind(1) == 1;
+    const int maxk = any_tf32 ? 64 : FF_MAX_K;
+    return (W == 32 || W == 64 || W == 128 || W == 256) && (K % 16 == 0) && K >= 16 && K <= maxk && (O % 16 == 0) && O >= 16 && O <= 128 && H >= 1;
 }
 
 // in2 != nullptr: channels [K1, K) come from a second tensor (the two halves of a channel concat read in place)
@@ -609,6 +613,7 @@ int run_ff(const sifnn::BnTail* tail, int pad, const float* in, const float* in2
     // output groups per CTA: two where the weights fit; TF32 with 64 input channels keeps one (8 chunks of weights + operand ring)
     int NG = (O >= 32) ? 2 : 1;
     if (kind == 1 && K > 32) NG = 1;
+    if (K > 64) NG = 1;
     const int gy = O / (16 * NG);
     int gx = sifnn::num_sms() / gy;
     if (g_ff_max_ctas > 0 && gx > g_ff_max_ctas) gx = g_ff_max_ctas;   // tests: long strips on small inputs

@@ -124,3 +124,41 @@ def test_ff_rejects_unsupported():
     x, w = rnd(1, 16, 8, 96).cuda(), rnd(16, 16, 3, 3).cuda()
     with pytest.raises(sifnn_b200.SifnnError):
         ops.conv3x3_fwd_ff(x, w)
+
+
+@pytest.mark.parametrize("kind", [0, 2], ids=["bf16x3", "fp16x3"])
+@pytest.mark.parametrize("shape", [(1, 128, 64, 11, 64), (2, 128, 64, 64, 64), (2, 128, 32, 8, 32), (1, 128, 16, 5, 128), (3, 96, 64, 6, 64)])
+def test_ff_128_input_channels(shape, kind):
+    """65..128 input channels (the decoder's first convolution, 128 -> 64 @ 64^2): one output group per CTA, 16-bit splits only; forward with the
+    BatchNorm prologue and statistics, and the data gradient of a layer with that many OUTPUT channels (its K)."""
+    lib = _lib.load()
+    lib.sifnn_conv3x3_ff_config(kind, 0)
+    try:
+        B, Cin, Cout, H, W = shape
+        assert lib.sifnn_conv3x3_ff_supported(Cin, Cout, H, W)
+        x, w = rnd(B, Cin, H, W, seed=31), rnd(Cout, Cin, 3, 3, seed=32, scale=0.1)
+        sc, sh = 1 + 0.3 * rnd(Cin, seed=33), 0.2 * rnd(Cin, seed=34)
+        stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+        y = ops.conv3x3_fwd_ff(x.cuda(), w.cuda(), sc.cuda(), sh.cuda(), stats)
+        a = F.relu(x.double() * sc.double()[None, :, None, None] + sh.double()[None, :, None, None])
+        ref = ref_conv(a, w)
+        assert rel_err(y, ref) < TOL[kind]
+        assert rel_err(stats[:Cout], ref.sum((0, 2, 3))) < 1e-4
+        assert rel_err(ops.conv3x3_fwd_ff(x.cuda(), w.cuda()), ref_conv(x, w)) < TOL[kind]
+        # data gradient with K = 128: dy has Cin channels here, dx Cout
+        wt = rnd(Cin, Cout, 3, 3, seed=35, scale=0.1)           # a layer Cout -> Cin
+        dy = rnd(B, Cin, H, W, seed=36)
+        xx = torch.zeros(B, Cout, H, W, dtype=torch.float64, requires_grad=True)
+        (ref_conv(xx, wt) * dy.double()).sum().backward()
+        assert rel_err(ops.conv3x3_dgrad_ff(dy.cuda(), wt.cuda()), xx.grad) < TOL_DG[kind]
+    finally:
+        lib.sifnn_conv3x3_ff_config(2, 0)
+
+
+def test_ff_tf32_keeps_64_input_channels():
+    lib = _lib.load()
+    lib.sifnn_conv3x3_ff_config(1, 0)
+    try:
+        assert not lib.sifnn_conv3x3_ff_supported(128, 64, 64, 64) and lib.sifnn_conv3x3_ff_supported(64, 64, 64, 64)
+    finally:
+        lib.sifnn_conv3x3_ff_config(2, 0)
