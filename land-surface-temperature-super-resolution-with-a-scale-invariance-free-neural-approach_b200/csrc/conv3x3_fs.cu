@@ -660,7 +660,7 @@ int run_fs(const sifnn::BnTail* tail, int pad, const float* in, const float* in2
     a.K1 = in2 ? K1 : K;
     a.trace = g_fs_trace;
     if (tail && stats) a.tail = *tail;
-    { const char* e = getenv("SIFNN_FS_ABLATE"); a.ablate = e ? atoi(e) : 0; }
+    { static int ablate = -1; if (ablate < 0) { const char* e = getenv("SIFNN_FS_ABLATE"); ablate = e ? atoi(e) : 0; } a.ablate = ablate; }   // read once per process
     const int NG = fs_groups(K, O, kind);
     const int gy = O / (16 * NG);
     int gx = sifnn::num_sms() / gy;
