@@ -13,6 +13,7 @@ per-GPU batch stays 32 (weak scaling, data parallel, two-bucket NCCL all-reduce)
 port -- the reference is pure Python/PyTorch and cannot travel to the GPU box) on the host cores.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -299,7 +300,10 @@ def kernel_rooflines(batch, fp32_peak, hbm_gbs, bf16_tflops, tf32_tflops, forwar
                 else:
                     add("dgrad_from1_kernel 16->1 (dgrad, SIMT)", "fp32", timed(lambda: _lib.call("sifnn_conv3x3_dgrad", P(dy), P(w), P(dx), 0, batch, ci, co, hw, hw, st)), fl, by)
             if use_tc and co > 1 and lib.sifnn_conv3x3_wgrad_km_supported(ci, co, hw, hw):   # the plan's rule (modelb.cu wgrad)
-                add("wgrad_km_kernel (BF16 split)", "tensor16", timed(lambda: _lib.call("sifnn_conv3x3_wgrad_km", P(x), None, None, P(dy), P(dw), P(ws), batch, ci, co, hw, hw, st)), fl, by)
+                # the kernel itself, like in the network plan, where the per-CTA partials of all layers are summed by one launch per backward phase
+                slots = ctypes.c_int(0)
+                add("wgrad_km_kernel (BF16 split)", "tensor16", timed(lambda: _lib.call("sifnn_conv3x3_wgrad_km_partials", P(x), None, None, P(dy), P(ws), batch, ci, co, hw, hw, st, ctypes.addressof(slots))), fl, by)
+                _lib.call("sifnn_wgrad_reduce", P(ws), P(dw), co * ci * 9, slots.value, st)
             elif use_tc and lib.sifnn_conv3x3_wgrad_tc_supported(ci, co, hw, hw):
                 add("wgrad_tc_kernel (TF32 split)", "tensor32", timed(lambda: _lib.call("sifnn_conv3x3_wgrad_tc", P(x), None, None, P(dy), P(dw), P(ws), batch, ci, co, hw, hw, st)), fl, by)
             else:

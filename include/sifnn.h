@@ -127,14 +127,21 @@ int sifnn_conv3x3_wgrad_tc(const float* in, const float* in_scale, const float* 
                            const float* dy, float* dw, void* workspace,
                            int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);
 
-/* Weight gradient with 16-bit K-major operands (csrc/wgrad_km.cu, round 2): 16 pixels per MMA, all nine taps and all hi/lo products in ONE MMA per
- * K step (M = 3 input rows x hi/lo x channels, N = 3 column-shifted dy copies x hi/lo x channels); activations split in FP16 (22 significant bits), gradients
- * in BF16 (16 bits, fp32 exponent range).  Same result contract as sifnn_conv3x3_wgrad_tc.  Shapes: Cin, Cout = 16 or a multiple of 32 (up to 256),
- * W a multiple of 32, H a multiple of 8 / 4 / 2 (rows per tile).  workspace: sifnn_conv3x3_wgrad_km_workspace() bytes.
- * sifnn_conv3x3_wgrad_km_config(fmt_x, fmt_dy): 0 = FP16, 1 = BF16 per operand (defaults 0, 1). */
+/* Weight gradient with 16-bit K-major operands (csrc/wgrad_km.cu, round 2; autograd of nn.Conv2d at model.py:135 w.r.t. the weight): 16 pixels per
+ * MMA, all nine taps and all hi/lo products of two dy rows in ONE MMA per K step (M = 4 input rows x hi/lo x channels, N = 2 rows x 3 column-shifted
+ * dy copies x hi/lo x channels).  Both operands are split hi + lo in BF16 (16 significant bits, fp32 exponent range); kind::f16 takes one format for
+ * both operands of an MMA (FP16 x BF16 faults), sifnn_conv3x3_wgrad_km_config(fmt_x, fmt_dy) with 0 = FP16, 1 = BF16 exists for experiments
+ * (defaults 1, 1; 0, 0 is 10x more accurate but only safe for gradients of O(1) magnitude).
+ * Same result contract as sifnn_conv3x3_wgrad_tc.  Shapes: Cin, Cout = 16 or a multiple of 32 (up to 256), W a multiple of 32, H a multiple of
+ * 8 / 4 / 2 (rows per tile).  workspace: sifnn_conv3x3_wgrad_km_workspace() bytes.
+ * Two-step form (what the network plan uses): sifnn_conv3x3_wgrad_km_partials leaves per-CTA partial sums [*slots][Cout*Cin*9] in `workspace`;
+ * sifnn_wgrad_reduce sums them in a fixed order (deterministic) into dw. */
 int sifnn_conv3x3_wgrad_km_supported(int Cin, int Cout, int H, int W);
 size_t sifnn_conv3x3_wgrad_km_workspace(int B, int Cin, int Cout, int H, int W);
 void sifnn_conv3x3_wgrad_km_config(int fmt_x, int fmt_dy);
+int sifnn_conv3x3_wgrad_km_partials(const float* in, const float* in_scale, const float* in_shift, const float* dy, void* workspace,
+                                    int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream, int* slots);
+int sifnn_wgrad_reduce(const float* partial, float* dw, int n, int slots, sifnn_stream_t stream);
 int sifnn_conv3x3_wgrad_km(const float* in, const float* in_scale, const float* in_shift,
                            const float* dy, float* dw, void* workspace,
                            int B, int Cin, int Cout, int H, int W, sifnn_stream_t stream);

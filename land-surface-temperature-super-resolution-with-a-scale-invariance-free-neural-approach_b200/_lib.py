@@ -93,6 +93,8 @@ SIGNATURES = {
     "sifnn_conv3x3_wgrad_km_workspace": (c_size_t, [c_int] * 5),
     "sifnn_conv3x3_wgrad_km_config": (None, [c_int, c_int]),
     "sifnn_conv3x3_wgrad_km": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
+    "sifnn_conv3x3_wgrad_km_partials": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p, c_void_p]),
+    "sifnn_wgrad_reduce": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "sifnn_bn_train_finalize": (c_int, [c_void_p] * 9 + [c_int, c_double, c_void_p]),
     "sifnn_bn_eval_affine": (c_int, [c_void_p] * 6 + [c_int, c_void_p]),
     "sifnn_bn_relu_bwd_reduce": (c_int, [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),

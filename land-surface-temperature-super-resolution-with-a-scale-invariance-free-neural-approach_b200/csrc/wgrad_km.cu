@@ -461,3 +461,15 @@ extern "C" int sifnn_conv3x3_wgrad_km(const float* in, const float* in_scale, co
     wgrad_km_reduce_kernel<<<(n + 31) / 32, 1024, 0, st>>>(static_cast<const float*>(workspace), dw, n, S);
     return sifnn::check_launch("wgrad_km_reduce_kernel");
 }
+
+extern "C" int sifnn_conv3x3_wgrad_km_partials(const float* in, const float* in_scale, const float* in_shift, const float* dy, void* workspace, int B, int Cin,
+                                               int Cout, int H, int W, sifnn_stream_t stream, int* slots) {
+    SIFNN_REQUIRE(slots, "conv3x3_wgrad_km_partials: null pointer");
+    return sifnn::wgrad_km_partials(in, in_scale, in_shift, dy, workspace, B, Cin, Cout, H, W, sifnn::as_stream(stream), slots);
+}
+
+extern "C" int sifnn_wgrad_reduce(const float* partial, float* dw, int n, int slots, sifnn_stream_t stream) {
+    SIFNN_REQUIRE(partial && dw && n > 0 && slots > 0, "wgrad_reduce: bad arguments");
+    const sifnn::ReduceJob job{partial, dw, n, slots};
+    return sifnn::wgrad_reduce_many(&job, 1, sifnn::as_stream(stream));
+}

@@ -72,3 +72,20 @@ def test_km_wgrad_rejects_unsupported():
         ops.conv3x3_wgrad_km(rnd(1, 8, 8, 32).cuda(), rnd(1, 16, 8, 32).cuda())
     with pytest.raises(sifnn_b200.SifnnError):
         ops.conv3x3_wgrad_km(rnd(1, 16, 8, 48).cuda(), rnd(1, 16, 8, 48).cuda())
+
+
+def test_km_two_step_form_equals_the_one_call_form():
+    """sifnn_conv3x3_wgrad_km_partials + sifnn_wgrad_reduce (what the network plan uses, reduces batched per backward phase) == sifnn_conv3x3_wgrad_km."""
+    import ctypes
+    lib = _lib.load()
+    for (B, Cin, Cout, H, W) in [(2, 16, 16, 8, 64), (2, 32, 16, 8, 64), (1, 64, 32, 4, 128)]:
+        x, dy = rnd(B, Cin, H, W, seed=41).cuda(), rnd(B, Cout, H, W, seed=42).cuda()
+        ref = ops.conv3x3_wgrad_km(x, dy)
+        ws = torch.empty(lib.sifnn_conv3x3_wgrad_km_workspace(B, Cin, Cout, H, W), dtype=torch.uint8, device="cuda")
+        dw = torch.full((Cout, Cin, 3, 3), float("nan"), device="cuda")
+        slots = ctypes.c_int(0)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.call("sifnn_conv3x3_wgrad_km_partials", x.data_ptr(), None, None, dy.data_ptr(), ws.data_ptr(), B, Cin, Cout, H, W, st, ctypes.addressof(slots))
+        assert slots.value > 0
+        _lib.call("sifnn_wgrad_reduce", ws.data_ptr(), dw.data_ptr(), Cout * Cin * 9, slots.value, st)
+        assert torch.equal(dw, ref)
