@@ -56,15 +56,17 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
 __global__ void __launch_bounds__(256) bn_relu_bwd_reduce_kernel(const float* __restrict__ dY, const float* __restrict__ raw,
                                                                  const float* __restrict__ scale, const float* __restrict__ shift,
                                                                  const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                                 double* sums, int C, int HW) {
-    const int c = blockIdx.y, b = blockIdx.z;
+                                                                 double* sums, int C, int HW, int reverse) {
+    const int c = reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int b = reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    const int bx = reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
     const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
     const size_t base = ((size_t)b * C + c) * HW;
     const float4* g4 = reinterpret_cast<const float4*>(dY + base);
     const float4* x4 = reinterpret_cast<const float4*>(raw + base);
     float s1 = 0.f, s2 = 0.f;
     const int n4 = HW >> 2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    for (int i = bx * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
         const float4 g = __ldg(g4 + i), x = __ldg(x4 + i);
         const float gv[4] = {g.x, g.y, g.z, g.w}, xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -537,6 +539,14 @@ extern "C" int sifnn_bn_eval_affine(const float* gamma, const float* beta, const
     return sifnn::check_launch("bn_eval_affine_kernel");
 }
 
+// SIFNN_BN_REVERSE: 0 both passes front to back; 1 (default) apply back to front (starts with what reduce left in L2); 2 reduce back to front
+// (starts with what the producer of dY left in L2), apply front to back
+static int bn_bwd_order() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SIFNN_BN_REVERSE"); v = e ? atoi(e) : 1; if (v < 0 || v > 2) v = 1; }
+    return v;
+}
+
 static int bn_bwd_chunks(int B, int C, int HW) {
     const int n4 = HW / 4;
     long long want = (long long)sifnn::num_sms() * 8 / ((long long)B * C) + 1;
@@ -552,7 +562,7 @@ extern "C" int sifnn_bn_relu_bwd_reduce(const float* dY, const float* raw, const
     SIFNN_REQUIRE(dY && raw && scale && shift && save_mean && save_invstd && sums, "bn_relu_bwd_reduce: null pointer");
     SIFNN_REQUIRE(B > 0 && C > 0 && HW > 0 && HW % 4 == 0 && B <= 65535 && C <= 65535, "bn_relu_bwd_reduce: bad shape (HW must be a multiple of 4)");
     dim3 grid(bn_bwd_chunks(B, C, HW), C, B);
-    bn_relu_bwd_reduce_kernel<<<grid, 256, 0, sifnn::as_stream(stream)>>>(dY, raw, scale, shift, save_mean, save_invstd, sums, C, HW);
+    bn_relu_bwd_reduce_kernel<<<grid, 256, 0, sifnn::as_stream(stream)>>>(dY, raw, scale, shift, save_mean, save_invstd, sums, C, HW, bn_bwd_order() == 2 ? 1 : 0);
     return sifnn::check_launch("bn_relu_bwd_reduce_kernel");
 }
 
@@ -562,8 +572,7 @@ extern "C" int sifnn_bn_relu_bwd_apply(const float* dY, const float* raw, const 
     SIFNN_REQUIRE(dY && raw && scale && shift && save_mean && save_invstd && gamma && sums && dx, "bn_relu_bwd_apply: null pointer");
     SIFNN_REQUIRE(B > 0 && C > 0 && HW > 0 && HW % 4 == 0 && B <= 65535 && C <= 65535, "bn_relu_bwd_apply: bad shape (HW must be a multiple of 4)");
     dim3 grid(bn_bwd_chunks(B, C, HW), C, B);
-    static int reverse = -1;   // SIFNN_BN_REVERSE=0 restores the front-to-back walk (A/B runs)
-    if (reverse < 0) { const char* e = getenv("SIFNN_BN_REVERSE"); reverse = (e && e[0] == '0') ? 0 : 1; }
+    const int reverse = bn_bwd_order() == 1 ? 1 : 0;
     bn_relu_bwd_apply_kernel<<<grid, 256, 0, sifnn::as_stream(stream)>>>(dY, raw, scale, shift, save_mean, save_invstd, gamma, sums, dx, dgamma, dbeta, C, HW,
                                                                            1.0 / ((double)B * HW), reverse);
     return sifnn::check_launch("bn_relu_bwd_apply_kernel");
