@@ -142,6 +142,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
 template <int KIND, int NG, int PAD, bool AFFINE, bool STATS, bool T2, bool DBG>
 __global__ void __launch_bounds__(FF_THREADS, 1) conv3x3_ff_kernel(const FfArgs a, const __grid_constant__ CUtensorMap tmap,
                                                                    const __grid_constant__ CUtensorMap tmap2) {
+    sifnn::pdl_wait_and_trigger();   // launched with launch_pdl: every global access below comes after the previous kernel of the stream
     constexpr int KC = (KIND == 1) ? 8 : 16;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int nchunks = a.K / KC;
@@ -568,7 +569,7 @@ int launch_ff(const FfArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, i
     }
     SIFNN_REQUIRE(L.total <= 227 * 1024, "conv3x3_ff: shared-memory budget exceeded (K=%d)", a.K);
     SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    kern<<<dim3(gx, gy), FF_THREADS, L.total, st>>>(a, tm1, tm2);
+    SIFNN_CUDA(sifnn::launch_pdl(kern, dim3(gx, gy), dim3(FF_THREADS), (size_t)L.total, st, a, tm1, tm2));
     return sifnn::check_launch("conv3x3_ff_kernel");
 }
 

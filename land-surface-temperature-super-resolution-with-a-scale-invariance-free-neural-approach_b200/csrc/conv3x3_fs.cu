@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(fs_threads(PAD, NG), 1) conv3x3_fs_kernel(cons
     constexpr int NSLOT = (NG == 1) ? 5 : 2;     // TMEM ring: 96 NG columns per row piece
     constexpr int SLOT = 96 * NG, HALF = 48 * NG;
     constexpr int W_TILE = 2 * SLOT * 16;        // bytes of the weight tile of one (chunk, kx)
+    sifnn::pdl_wait_and_trigger();   // launched with launch_pdl: every global access below comes after the previous kernel of the stream
     extern __shared__ __align__(1024) unsigned char smem[];
     const int nchunks = a.K / KC;
     const FsLayout L = fs_layout(nchunks, NG, KC, PAD == 1);
@@ -613,7 +614,7 @@ int launch_fs(const FsArgs& a, const CUtensorMap& tm1, const CUtensorMap& tm2, i
     }
     SIFNN_REQUIRE(L.total <= 227 * 1024, "conv3x3_fs: shared-memory budget exceeded (K=%d)", a.K);
     SIFNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    kern<<<dim3(gx, gy), fs_threads(PAD, NG), L.total, st>>>(a, tm1, tm2);
+    SIFNN_CUDA(sifnn::launch_pdl(kern, dim3(gx, gy), dim3(fs_threads(PAD, NG)), (size_t)L.total, st, a, tm1, tm2));
     return sifnn::check_launch("conv3x3_fs_kernel");
 }
 

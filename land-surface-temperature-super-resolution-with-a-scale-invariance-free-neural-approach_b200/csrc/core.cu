@@ -52,6 +52,12 @@ int tc_split_kind(int dgrad) {
 }
 void tc_split_set(int fwd_kind, int dgrad_kind) { g_split[0] = fwd_kind; g_split[1] = dgrad_kind; }
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SIFNN_PDL"); v = (e && e[0] == '1') ? 1 : 0; }   // OFF by default: measured slower, see common.cuh
+    return v == 1;
+}
+
 int num_sms() {   // of the CURRENT device (cached per device)
     static int cache[128] = {0};
     int dev = 0;

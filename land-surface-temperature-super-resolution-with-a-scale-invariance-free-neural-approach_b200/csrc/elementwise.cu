@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_reduce_kernel(const float* __
                                                                  const float* __restrict__ scale, const float* __restrict__ shift,
                                                                  const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                  double* sums, int C, int HW, int reverse) {
+    sifnn::pdl_wait_and_trigger();
     const int c = reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
     const int b = reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
     const int bx = reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const float* __restrict__ gamma, const double* __restrict__ sums,
                                                                 float* dx, float* dgamma, float* dbeta, int C, int HW, double inv_n, int reverse) {
+    sifnn::pdl_wait_and_trigger();
     // reverse = 1: walk the tensors from the end.  The reduce pass that ran just before read dY and raw front to back, so their tails are what the
     // 126 MB L2 still holds; on the 256^2 layers (2 x 134 MB) a front-to-back second pass would miss everywhere.
     const int c = reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
@@ -562,7 +564,8 @@ extern "C" int sifnn_bn_relu_bwd_reduce(const float* dY, const float* raw, const
     SIFNN_REQUIRE(dY && raw && scale && shift && save_mean && save_invstd && sums, "bn_relu_bwd_reduce: null pointer");
     SIFNN_REQUIRE(B > 0 && C > 0 && HW > 0 && HW % 4 == 0 && B <= 65535 && C <= 65535, "bn_relu_bwd_reduce: bad shape (HW must be a multiple of 4)");
     dim3 grid(bn_bwd_chunks(B, C, HW), C, B);
-    bn_relu_bwd_reduce_kernel<<<grid, 256, 0, sifnn::as_stream(stream)>>>(dY, raw, scale, shift, save_mean, save_invstd, sums, C, HW, bn_bwd_order() == 2 ? 1 : 0);
+    SIFNN_CUDA(sifnn::launch_pdl(bn_relu_bwd_reduce_kernel, grid, dim3(256), (size_t)0, sifnn::as_stream(stream), dY, raw, scale, shift, save_mean, save_invstd, sums, C, HW,
+                                 bn_bwd_order() == 2 ? 1 : 0));
     return sifnn::check_launch("bn_relu_bwd_reduce_kernel");
 }
 
@@ -573,8 +576,8 @@ extern "C" int sifnn_bn_relu_bwd_apply(const float* dY, const float* raw, const 
     SIFNN_REQUIRE(B > 0 && C > 0 && HW > 0 && HW % 4 == 0 && B <= 65535 && C <= 65535, "bn_relu_bwd_apply: bad shape (HW must be a multiple of 4)");
     dim3 grid(bn_bwd_chunks(B, C, HW), C, B);
     const int reverse = bn_bwd_order() == 1 ? 1 : 0;
-    bn_relu_bwd_apply_kernel<<<grid, 256, 0, sifnn::as_stream(stream)>>>(dY, raw, scale, shift, save_mean, save_invstd, gamma, sums, dx, dgamma, dbeta, C, HW,
-                                                                           1.0 / ((double)B * HW), reverse);
+    SIFNN_CUDA(sifnn::launch_pdl(bn_relu_bwd_apply_kernel, grid, dim3(256), (size_t)0, sifnn::as_stream(stream), dY, raw, scale, shift, save_mean, save_invstd, gamma, sums, dx, dgamma, dbeta,
+                                 C, HW, 1.0 / ((double)B * HW), reverse));
     return sifnn::check_launch("bn_relu_bwd_apply_kernel");
 }
 

@@ -104,6 +104,7 @@ __device__ __forceinline__ void km_split8(const float* v, int fmt, uint4& hi, ui
 
 template <int CI, int CO, int R, bool AFFINE>
 __global__ void __launch_bounds__(KM_THREADS, 1) wgrad_km_kernel(const KmArgs a, const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy) {
+    sifnn::pdl_wait_and_trigger();   // launched with launch_pdl: every global access below comes after the previous kernel of the stream
     using C = KmCfg<CI, CO, R>;
     constexpr int TR = C::TR, G8 = C::G8, XR = C::XR, DR = C::DR, N = C::N, NSETS = C::NSETS, MB = C::MB, RS = C::RS;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -347,8 +348,7 @@ int launch_km(const float* in, const float* dy, KmArgs a, int S, bool affine, cu
                       encode_rows_of_planes_map(&td, dy, a.W, a.H, (long long)a.B * a.O, KM_DW, CO, R),
                   "conv3x3_wgrad_km: cuTensorMapEncodeTiled is unavailable or failed");
     dim3 grid(S, (a.K / CI) * a.nco);
-    if (affine) k_aff<<<grid, KM_THREADS, C::BYTES, st>>>(a, tx, td);
-    else k_pln<<<grid, KM_THREADS, C::BYTES, st>>>(a, tx, td);
+    SIFNN_CUDA(sifnn::launch_pdl(affine ? k_aff : k_pln, grid, dim3(KM_THREADS), (size_t)C::BYTES, st, a, tx, td));
     return sifnn::check_launch("wgrad_km_kernel");
 }
 
