@@ -102,18 +102,20 @@ int wgrad_reduce_many(const ReduceJob* jobs, int njobs, cudaStream_t st);
 // the previous kernel of the stream is still draining (launch latency and block scheduling overlap that kernel's tail) and block in
 // griddepcontrol.wait until the previous grid has completed and its memory is visible -- every global access comes after the wait, so the
 // semantics are those of ordinary stream order.  griddepcontrol.launch_dependents right after it lets the NEXT kernel do the same.
-// MEASURED (round 2, fs / ff / km / BatchNorm-backward kernels = ~80 of the 115 launches of a step): 4.274 ms with the attribute against 4.136 ms
-// without -- the early-scheduled CTAs of the next kernel cost more than the hidden launch latency inside a CUDA graph.  So the attribute is OFF by
-// default (the wait / trigger instructions are no-ops then) and SIFNN_PDL=1 turns it on for experiments.  (Kernels without the wait must keep
-// the <<< >>> launch.)
+// MEASURED (round 2, same-box A/B of the training step): attribute on the fs / ff / km / BatchNorm-backward kernels (~80 of 115 launches, SIFNN_PDL=1)
+// 4.274 ms against 4.136 ms without -- a persistent 226 KB CTA scheduled early next to the CTAs of an HBM-bound elementwise kernel takes their
+// occupancy.  Attribute on the BatchNorm-backward kernels only (SIFNN_PDL=2, the default): 4.115 against 4.134 ms -- their CTAs cannot co-reside with
+// the persistent kernels they follow, so only the launch gap disappears.  SIFNN_PDL=0 turns it off.  (Kernels without the wait must keep the
+// <<< >>> launch.)
 bool pdl_enabled();
+int pdl_mode();   // SIFNN_PDL: 0 off (default), 1 every converted kernel, 2 only the BatchNorm-backward kernels (dependents of the persistent kernels)
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait_and_trigger() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl_if(bool allow, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -121,10 +123,14 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = allow ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    return launch_pdl_if(pdl_mode() == 1, kern, grid, block, smem, st, args...);
 }
 #endif
 

@@ -52,11 +52,12 @@ int tc_split_kind(int dgrad) {
 }
 void tc_split_set(int fwd_kind, int dgrad_kind) { g_split[0] = fwd_kind; g_split[1] = dgrad_kind; }
 
-bool pdl_enabled() {
+int pdl_mode() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("SIFNN_PDL"); v = (e && e[0] == '1') ? 1 : 0; }   // OFF by default: measured slower, see common.cuh
-    return v == 1;
+    if (v < 0) { const char* e = getenv("SIFNN_PDL"); v = e ? atoi(e) : 2; if (v < 0 || v > 2) v = 2; }   // default 2: see common.cuh
+    return v;
 }
+bool pdl_enabled() { return pdl_mode() != 0; }
 
 int num_sms() {   // of the CURRENT device (cached per device)
     static int cache[128] = {0};

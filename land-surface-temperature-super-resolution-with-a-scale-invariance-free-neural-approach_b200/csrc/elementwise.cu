@@ -564,7 +564,7 @@ extern "C" int sifnn_bn_relu_bwd_reduce(const float* dY, const float* raw, const
     SIFNN_REQUIRE(dY && raw && scale && shift && save_mean && save_invstd && sums, "bn_relu_bwd_reduce: null pointer");
     SIFNN_REQUIRE(B > 0 && C > 0 && HW > 0 && HW % 4 == 0 && B <= 65535 && C <= 65535, "bn_relu_bwd_reduce: bad shape (HW must be a multiple of 4)");
     dim3 grid(bn_bwd_chunks(B, C, HW), C, B);
-    SIFNN_CUDA(sifnn::launch_pdl(bn_relu_bwd_reduce_kernel, grid, dim3(256), (size_t)0, sifnn::as_stream(stream), dY, raw, scale, shift, save_mean, save_invstd, sums, C, HW,
+    SIFNN_CUDA(sifnn::launch_pdl_if(sifnn::pdl_mode() != 0, bn_relu_bwd_reduce_kernel, grid, dim3(256), (size_t)0, sifnn::as_stream(stream), dY, raw, scale, shift, save_mean, save_invstd, sums, C, HW,
                                  bn_bwd_order() == 2 ? 1 : 0));
     return sifnn::check_launch("bn_relu_bwd_reduce_kernel");
 }
@@ -576,7 +576,7 @@ extern "C" int sifnn_bn_relu_bwd_apply(const float* dY, const float* raw, const 
     SIFNN_REQUIRE(B > 0 && C > 0 && HW > 0 && HW % 4 == 0 && B <= 65535 && C <= 65535, "bn_relu_bwd_apply: bad shape (HW must be a multiple of 4)");
     dim3 grid(bn_bwd_chunks(B, C, HW), C, B);
     const int reverse = bn_bwd_order() == 1 ? 1 : 0;
-    SIFNN_CUDA(sifnn::launch_pdl(bn_relu_bwd_apply_kernel, grid, dim3(256), (size_t)0, sifnn::as_stream(stream), dY, raw, scale, shift, save_mean, save_invstd, gamma, sums, dx, dgamma, dbeta,
+    SIFNN_CUDA(sifnn::launch_pdl_if(sifnn::pdl_mode() != 0, bn_relu_bwd_apply_kernel, grid, dim3(256), (size_t)0, sifnn::as_stream(stream), dY, raw, scale, shift, save_mean, save_invstd, gamma, sums, dx, dgamma, dbeta,
                                  C, HW, 1.0 / ((double)B * HW), reverse));
     return sifnn::check_launch("bn_relu_bwd_apply_kernel");
 }
