@@ -104,11 +104,12 @@ int wgrad_reduce_many(const ReduceJob* jobs, int njobs, cudaStream_t st);
 // semantics are those of ordinary stream order.  griddepcontrol.launch_dependents right after it lets the NEXT kernel do the same.
 // MEASURED (round 2, same-box A/B of the training step): attribute on the fs / ff / km / BatchNorm-backward kernels (~80 of 115 launches, SIFNN_PDL=1)
 // 4.274 ms against 4.136 ms without -- a persistent 226 KB CTA scheduled early next to the CTAs of an HBM-bound elementwise kernel takes their
-// occupancy.  Attribute on the BatchNorm-backward kernels only (SIFNN_PDL=2, the default): 4.115 against 4.134 ms -- their CTAs cannot co-reside with
-// the persistent kernels they follow, so only the launch gap disappears.  SIFNN_PDL=0 turns it off.  (Kernels without the wait must keep the
+// occupancy.  Attribute on the elementwise kernels that FOLLOW a persistent kernel only (SIFNN_PDL=2, the default: BatchNorm backward,
+// pooling, residual, up-sample + concat and their adjoints, the batched reduce): 4.095 against 4.121 ms -- their CTAs cannot co-reside with the
+// persistent kernels they follow, so only the launch gap disappears.  SIFNN_PDL=0 turns it off.  (Kernels without the wait must keep the
 // <<< >>> launch.)
 bool pdl_enabled();
-int pdl_mode();   // SIFNN_PDL: 0 off (default), 1 every converted kernel, 2 only the BatchNorm-backward kernels (dependents of the persistent kernels)
+int pdl_mode();   // SIFNN_PDL: 0 off, 1 every converted kernel, 2 (default) only the elementwise kernels that follow a persistent kernel
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait_and_trigger() {
     asm volatile("griddepcontrol.wait;" ::: "memory");

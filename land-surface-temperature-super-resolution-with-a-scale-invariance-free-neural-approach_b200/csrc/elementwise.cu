@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
 __global__ void __launch_bounds__(256) act_avgpool2_kernel(const float* __restrict__ raw, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, float* __restrict__ out,
                                                            long long total, int C, int H, int W) {
+    sifnn::pdl_wait_and_trigger();
     const int Ho = H >> 1, Wo = W >> 1, Wo2 = Wo >> 1;  // each thread: 2 output pixels = 4 input columns
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int xo2 = (int)(idx % Wo2);
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(256) act_avgpool2_kernel(const float* __restri
 
 // din (B,C,H,W) (+)= 0.25 * dout (B,C,H/2,W/2) replicated 2x2
 __global__ void __launch_bounds__(256) avgpool2_bwd_kernel(const float* __restrict__ dout, float* din, long long total, int H, int W, int accumulate) {
+    sifnn::pdl_wait_and_trigger();
     const int Ho = H >> 1, Wo = W >> 1, Wo2 = Wo >> 1;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int xo2 = (int)(idx % Wo2);
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(256) avgpool2_bwd_kernel(const float* __restri
 __global__ void __launch_bounds__(256) act_residual_kernel(const float* __restrict__ x, const float* __restrict__ raw,
                                                            const float* __restrict__ scale, const float* __restrict__ shift,
                                                            float* __restrict__ out, long long total4, int C, int HW4) {
+    sifnn::pdl_wait_and_trigger();
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
         const int c = (int)((idx / HW4) % C);
         const float sc = __ldg(scale + c), sh = __ldg(shift + c);
@@ -252,6 +255,7 @@ constexpr int UPC = 4;
 __global__ void __launch_bounds__(256, 2) act_upcat4_kernel(const float* __restrict__ low, const float* __restrict__ lsc, const float* __restrict__ lsh,
                                                             const float* __restrict__ skip, const float* __restrict__ ssc, const float* __restrict__ ssh,
                                                             float* __restrict__ out, int C1, int H, int W, float ry, float rx) {
+    sifnn::pdl_wait_and_trigger();
     const int Ho = 2 * H, Wo = 2 * W, Wq = Wo >> 2;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= Ho * Wq) return;
@@ -384,6 +388,7 @@ __device__ __forceinline__ void up_gather_weights(int i, int n_in, float r, floa
 template <int LR>
 __global__ void __launch_bounds__(256) upcat_bwd_low_tiled_kernel(const float* __restrict__ dout, float* __restrict__ dlow, float* __restrict__ dskip,
                                                                   int C1, int C2, int H, float ry, float rx) {
+    sifnn::pdl_wait_and_trigger();
     constexpr int W = 32 * LR, Wo = 2 * W, Wq = Wo / 4, STRIDE = Wo + 8;   // staged row: column x at index x + 4, zeros at -2, -1, Wo, Wo + 1
     __shared__ __align__(16) float in_s[UPB_NR * STRIDE];
     __shared__ float wy_s[UPB_TL][6];      // the y weights depend on the row only: one thread per low-resolution row computes them once
@@ -586,7 +591,7 @@ extern "C" int sifnn_act_avgpool2_fwd(const float* raw, const float* scale, cons
     SIFNN_REQUIRE(raw && scale && shift && out, "act_avgpool2_fwd: null pointer");
     SIFNN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 4 == 0, "act_avgpool2_fwd: need even H and W %% 4 == 0");
     const long long total = (long long)B * C * (H / 2) * (W / 4);
-    act_avgpool2_kernel<<<grid_for(total, 256), 256, 0, sifnn::as_stream(stream)>>>(raw, scale, shift, out, total, C, H, W);
+    SIFNN_CUDA(sifnn::launch_pdl_if(sifnn::pdl_mode() != 0, act_avgpool2_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, sifnn::as_stream(stream), raw, scale, shift, out, total, C, H, W));
     return sifnn::check_launch("act_avgpool2_kernel");
 }
 
@@ -594,7 +599,7 @@ extern "C" int sifnn_avgpool2_bwd(const float* dout, float* din, int accumulate,
     SIFNN_REQUIRE(dout && din, "avgpool2_bwd: null pointer");
     SIFNN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 4 == 0, "avgpool2_bwd: need even H and W %% 4 == 0");
     const long long total = (long long)B * C * (H / 2) * (W / 4);
-    avgpool2_bwd_kernel<<<grid_for(total, 256), 256, 0, sifnn::as_stream(stream)>>>(dout, din, total, H, W, accumulate ? 1 : 0);
+    SIFNN_CUDA(sifnn::launch_pdl_if(sifnn::pdl_mode() != 0, avgpool2_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, sifnn::as_stream(stream), dout, din, total, H, W, accumulate ? 1 : 0));
     return sifnn::check_launch("avgpool2_bwd_kernel");
 }
 
@@ -603,7 +608,7 @@ extern "C" int sifnn_act_residual_fwd(const float* x, const float* raw, const fl
     SIFNN_REQUIRE(x && raw && scale && shift && out, "act_residual_fwd: null pointer");
     SIFNN_REQUIRE(B > 0 && C > 0 && HW > 0 && HW % 4 == 0, "act_residual_fwd: HW must be a multiple of 4");
     const long long total4 = (long long)B * C * (HW / 4);
-    act_residual_kernel<<<grid_for(total4, 256), 256, 0, sifnn::as_stream(stream)>>>(x, raw, scale, shift, out, total4, C, HW / 4);
+    SIFNN_CUDA(sifnn::launch_pdl_if(sifnn::pdl_mode() != 0, act_residual_kernel, dim3(grid_for(total4, 256)), dim3(256), (size_t)0, sifnn::as_stream(stream), x, raw, scale, shift, out, total4, C, HW / 4));
     return sifnn::check_launch("act_residual_kernel");
 }
 
@@ -617,8 +622,8 @@ extern "C" int sifnn_act_upcat_fwd(const float* low, const float* low_scale, con
     SIFNN_REQUIRE(W % 2 == 0 && B <= 65535 && C1 + C2 <= 65535, "act_upcat_fwd: need even W, B and channels <= 65535");
     if (C1 == C2 && C1 % UPC == 0) {
         dim3 grid4((2 * H * (2 * W / 4) + 255) / 256, C1 / UPC, B);
-        act_upcat4_kernel<<<grid4, 256, 0, sifnn::as_stream(stream)>>>(low, low_scale, low_shift, skip, skip_scale, skip_shift, out, C1, H, W,
-                                                                        up_ratio(H), up_ratio(W));
+        SIFNN_CUDA(sifnn::launch_pdl_if(sifnn::pdl_mode() != 0, act_upcat4_kernel, grid4, dim3(256), (size_t)0, sifnn::as_stream(stream), low, low_scale, low_shift, skip, skip_scale, skip_shift, out, C1, H, W,
+                                        up_ratio(H), up_ratio(W)));
         return sifnn::check_launch("act_upcat4_kernel");
     }
     dim3 grid((2 * H * (2 * W / 4) + 255) / 256, C1 + C2, B);
@@ -635,9 +640,9 @@ extern "C" int sifnn_upcat_bwd(const float* dout, float* dlow, float* dskip, int
     if ((W == 32 || W == 64 || W == 128) && (long long)B * C1 <= 65535) {
         dim3 grid((H + UPB_TL - 1) / UPB_TL, B * C1);
         float* fused_skip = (C1 == C2) ? dskip : nullptr;
-        if (W == 128) upcat_bwd_low_tiled_kernel<4><<<grid, 256, 0, st>>>(dout, dlow, fused_skip, C1, C2, H, up_ratio(H), up_ratio(W));
-        else if (W == 64) upcat_bwd_low_tiled_kernel<2><<<grid, 256, 0, st>>>(dout, dlow, fused_skip, C1, C2, H, up_ratio(H), up_ratio(W));
-        else upcat_bwd_low_tiled_kernel<1><<<grid, 256, 0, st>>>(dout, dlow, fused_skip, C1, C2, H, up_ratio(H), up_ratio(W));
+        if (W == 128) SIFNN_CUDA(sifnn::launch_pdl_if(sifnn::pdl_mode() != 0, upcat_bwd_low_tiled_kernel<4>, grid, dim3(256), (size_t)0, st, dout, dlow, fused_skip, C1, C2, H, up_ratio(H), up_ratio(W)));
+        else if (W == 64) SIFNN_CUDA(sifnn::launch_pdl_if(sifnn::pdl_mode() != 0, upcat_bwd_low_tiled_kernel<2>, grid, dim3(256), (size_t)0, st, dout, dlow, fused_skip, C1, C2, H, up_ratio(H), up_ratio(W)));
+        else SIFNN_CUDA(sifnn::launch_pdl_if(sifnn::pdl_mode() != 0, upcat_bwd_low_tiled_kernel<1>, grid, dim3(256), (size_t)0, st, dout, dlow, fused_skip, C1, C2, H, up_ratio(H), up_ratio(W)));
         if (fused_skip) return sifnn::check_launch("upcat_bwd_low_tiled_kernel");
         SIFNN_TRY(sifnn::check_launch("upcat_bwd_low_tiled_kernel"));
     } else {

@@ -414,6 +414,7 @@ int wgrad_km_partials(const float* in, const float* in_scale, const float* in_sh
 // out[i] = sum_s partial[s][i] for up to REDUCE_MAX_JOBS (layer) jobs in one launch; block -> job by a prefix table
 struct ReduceTable { ReduceJob j[REDUCE_MAX_JOBS]; int first_block[REDUCE_MAX_JOBS + 1]; int njobs; };
 __global__ void __launch_bounds__(1024) wgrad_reduce_many_kernel(const ReduceTable t) {
+    sifnn::pdl_wait_and_trigger();
     __shared__ float red[32][33];
     int k = 0;
     while (k + 1 < t.njobs && (int)blockIdx.x >= t.first_block[k + 1]) ++k;
@@ -445,7 +446,7 @@ int wgrad_reduce_many(const ReduceJob* jobs, int njobs, cudaStream_t st) {
     }
     t.first_block[njobs] = blocks;
     t.njobs = njobs;
-    wgrad_reduce_many_kernel<<<blocks, 1024, 0, st>>>(t);
+    SIFNN_CUDA(launch_pdl_if(pdl_mode() != 0, wgrad_reduce_many_kernel, dim3(blocks), dim3(1024), (size_t)0, st, t));
     return check_launch("wgrad_reduce_many_kernel");
 }
 
